@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- the warping hot path on B200, measured the way BASELINE.json asks.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path
+    python bench.py --impl reference [...]                        the reference's CPU path
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on):
+fused block_extractor + local_attn_reshape + softmax ("ExtractorAttn tail",
+model/networks/base_function.py:804-810), forward + backward, per GPU
+B=16, C=256, 256x256, k=5, bf16 data / fp32 flow, synthetic smooth flow.
+One step = one forward + one backward over that batch.  Weak scaling: every rank
+owns its own B=16 batch shard (the path has no cross-sample dependence, so there is
+no data-path collective; see gfla_b200/sharding.py).
+
+Printed JSON (one line, rank 0):
+  value      Mpixels/s (B*H*W output pixels, fwd+bwd) with inputs resident in HBM,
+             whole job (sum over ranks / max-over-ranks device time)
+  e2e        same metric through the public autograd API with HOST (pinned) buffers:
+             H2D of source/flow/logits/grad_out and D2H of out + the three gradients
+             inside the timed region
+  roofline   dominant kernel of the step: algorithmic bytes / CUDA-event duration vs
+             the measured HBM peak (MEASURED_PEAKS.json); roofline_fwd: the fused forward
+  cpu_baseline  the reference's own kernel bodies on the host cores (oracle/_ref),
+             bounded sample, rank 0 / N=1 only
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "warp-layer Mpixels/s (fwd+bwd) @256^2 C=256 k=5"
+UNIT = "Mpixels/s"
+CFG = dict(B=16, C=256, H=256, W=256, k=5)
+
+
+# ----------------------------------------------------------------------------- helpers
+def algorithmic_bytes(B, C, H, W, k, elt=2):
+    """SURVEY.md 8(d) / BASELINE.md section 2, bf16 data + fp32 flow.
+    fwd: read source, write out (C*elt each), read flow (2*4), read logits (k*k*elt)
+    bwd: read grad_out, source (C*elt each), flow, logits; write grad_source (C*elt), grad_flow (8), grad_logits"""
+    px = B * H * W
+    fwd = 2 * C * elt + 8 + k * k * elt
+    bwd = 3 * C * elt + 8 + k * k * elt + 8 + k * k * elt
+    return px * fwd, px * bwd
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def make_inputs(torch, dev, B, C, H, W, k, seed, flow_kind="smooth"):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    src = torch.randn(B, C, H, W, generator=g).bfloat16()
+    if flow_kind == "smooth":   # bilinear x16 up-sampling of U(-8,8) noise
+        coarse = torch.rand(B, 2, H // 16, W // 16, generator=g) * 16 - 8
+        flow = torch.nn.functional.interpolate(coarse, size=(H, W), mode="bilinear", align_corners=True).contiguous()
+    else:
+        flow = torch.rand(B, 2, H, W, generator=g) * 16 - 8
+    logits = torch.randn(B, k * k, H, W, generator=g).bfloat16()
+    gout = torch.randn(B, C, H, W, generator=g).bfloat16()
+    return src, flow.float(), logits, gout
+
+
+# ----------------------------------------------------------------------------- CPU reference leg
+def cpu_reference_run(steps, warmup, budget_s, full=True):
+    """Times the reference's CPU implementation of the path (its own kernel bodies compiled
+    for the host + torch CPU ops for softmax/mul/avg_pool, oracle/ref_pipeline.py) on a bounded
+    sample of the cfg2 workload: B=1, full C=256, k=5, a strip of R rows x 256 columns, fp32
+    (the reference has no bf16).  Returns per-step seconds and the sample description."""
+    import numpy as np
+    import torch
+    import oracle.oracle as orc
+    from oracle.ref_pipeline import local_attn_fwd_bwd
+    if orc.have_ref():
+        lib, kind = orc.Ref(), "reference"
+        cores = lib.max_threads()
+    else:
+        orc.build(ref=False)
+        lib, kind, cores = orc.Oracle(), "port", 1
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    C, W, k = CFG["C"], CFG["W"], CFG["k"]
+    rng = np.random.default_rng(0)
+    src = rng.standard_normal((1, C, CFG["H"], W)).astype(np.float32)
+
+    def run(rows):
+        flow = rng.uniform(-8, 8, (1, 2, rows, W)).astype(np.float32)
+        logits = rng.standard_normal((1, k * k, rows, W)).astype(np.float32)
+        g = rng.standard_normal((1, C, rows, W)).astype(np.float32)
+        t = time.perf_counter()
+        local_attn_fwd_bwd(lib, src, flow, logits, g, k)
+        return time.perf_counter() - t
+
+    probe_rows = 4
+    run(probe_rows)                                    # page-in / thread pool warm-up
+    per_row = run(probe_rows) / probe_rows
+    n = max(1, steps + warmup)
+    rows = int(max(2, min(CFG["H"], budget_s / n / max(per_row, 1e-9))))
+    for _ in range(warmup):
+        run(rows)
+    times = [run(rows) for _ in range(steps)]
+    sec = sum(times) / len(times)
+    mpx = rows * W / sec / 1e6
+    return {"value": mpx, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"B=1 C={C} k={k} fp32, strip of {rows} rows x {W} cols of the 256x256 map, fwd+bwd, "
+                      f"{steps} steps (+{warmup} warm-up), unfused reference pipeline"}, sec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--flow", default="smooth", choices=["smooth", "iid"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "gather", "tile"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    B, C, H, W, k = (CFG[x] for x in "BCHWk")
+    config = {"workload": f"cfg2: fused block_extractor+local_attn_reshape+softmax fwd+bwd, per-GPU B={B} C={C} "
+                          f"{H}x{W} k={k}, bf16 data / fp32 flow ({args.flow} flow)",
+              "per_gpu_batch": B, "global_batch": B * world, "C": C, "H": H, "W": W, "k": k,
+              "flow": args.flow, "sharding": f"batch x{world} (no data-path collective)",
+              "l2": "inputs (>=1 GiB per step) exceed the 126 MB L2; no explicit flush"}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps, warmup = max(1, args.steps), max(0, args.warmup)
+        cb, sec = cpu_reference_run(steps, warmup, budget_s=150.0)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import gfla_b200
+    from gfla_b200 import functional as F_
+    from gfla_b200 import _lib
+    from gfla_b200.sharding import reduce_max_time
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.lib().gfla_device_check(), "device check")
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+
+    src_h, flow_h, logits_h, gout_h = make_inputs(torch, dev, B, C, H, W, k, seed=1234 + rank, flow_kind=args.flow)
+    src, flow, logits, gout = (t.to(dev) for t in (src_h, flow_h, logits_h, gout_h))
+
+    def step(record=None):
+        if record is not None:
+            record[0].record()
+        out = F_.local_attn_fwd(src, flow, logits, k, algo=args.algo)
+        if record is not None:
+            record[1].record()
+        grads = F_.local_attn_bwd(src, flow, logits, gout, k)
+        if record is not None:
+            record[2].record()
+        return out, grads
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize(dev)
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    barrier()
+    t_wall0 = time.time()
+    for i in range(steps):
+        step(ev[i])
+    barrier()
+    t_wall1 = time.time()
+    total_ms = ev[0][0].elapsed_time(ev[-1][2])
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
+    total_ms = reduce_max_time(total_ms, dev)
+    ms_per_step = total_ms / steps
+    value = world * B * H * W / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: public autograd API, host buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda t: t.pin_memory()
+        hs, hf, hl, hg = pin(src_h), pin(flow_h), pin(logits_h), pin(gout_h)
+        ho = torch.empty_like(hs).pin_memory()
+        hgs, hgf, hgl = torch.empty_like(hs).pin_memory(), torch.empty_like(hf).pin_memory(), torch.empty_like(hl).pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in (hs, hf, hl, hg))
+        d2h = sum(t.numel() * t.element_size() for t in (ho, hgs, hgf, hgl))
+
+        def e2e_step():
+            s = hs.to(dev, non_blocking=True).requires_grad_()
+            f = hf.to(dev, non_blocking=True).requires_grad_()
+            l = hl.to(dev, non_blocking=True).requires_grad_()
+            g = hg.to(dev, non_blocking=True)
+            out = gfla_b200.local_attention(s, f, l, k)          # the call a user makes
+            out.backward(g)
+            ho.copy_(out.detach(), non_blocking=True)
+            hgs.copy_(s.grad, non_blocking=True)
+            hgf.copy_(f.grad, non_blocking=True)
+            hgl.copy_(l.grad, non_blocking=True)
+
+        e2e_steps = steps
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        b_.record()
+        barrier()
+        e2e_ms = reduce_max_time(a.elapsed_time(b_), dev) / e2e_steps
+        e2e = {"value": world * B * H * W / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps}
+    if rank == 0:
+        sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_kind = measured_peak_gbs()
+    fwd_bytes, bwd_bytes = algorithmic_bytes(B, C, H, W, k)
+
+    def roof(nbytes, ms, kernel):
+        ach = nbytes / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "peak_source": peak_kind, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "algorithmic_bytes": nbytes, "launch_ms": ms}
+
+    rf_fwd = roof(fwd_bytes, fwd_ms, "local_attn_fwd")
+    rf_bwd = roof(bwd_bytes, bwd_ms, "local_attn_bwd (+grad_source memset)")
+    dominant = rf_bwd if bwd_ms >= fwd_ms else rf_fwd
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": config,
+            "roofline": dominant, "roofline_fwd": rf_fwd, "roofline_bwd": rf_bwd,
+            "step_roofline_frac": (fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9 / peak,
+            "clocks": sampler.summary(t_wall0, t_wall1),
+            "gpu_launches": 2 * steps, "e2e": e2e}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cb, _ = cpu_reference_run(steps=2, warmup=0, budget_s=20.0)
+            line["cpu_baseline"] = cb
+        except Exception as exc:  # the baseline leg must never take the bench line down
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(exc)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,138 @@
+// extern "C" surface of libgfla_warp.so (declared in include/gfla_warp.h):
+// argument validation + dispatch; no state, no allocation.
+#include "common.cuh"
+
+namespace gfla {
+int block_extract_fwd(const void*, const void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int block_extract_bwd(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int attn_reshape_fwd(const void*, void*, int, int, int, int, int, cudaStream_t);
+int attn_reshape_bwd(const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int resample2d_fwd(const void*, const void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int resample2d_bwd(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int local_attn_fwd_gather(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int local_attn_bwd_gather(const void*, const void*, const void*, const void*, void*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int local_attn_fwd_tc(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+bool local_attn_fwd_tc_supported(int B, int C, int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, const void* src, const void* out);
+}  // namespace gfla
+
+using namespace gfla;
+
+#define REQ_PTR(p) do { if ((p) == nullptr) return GFLA_E_NULL; } while (0)
+#define REQ_ALIGN(p, dt) do { if (!aligned((p), elem_size(dt))) return GFLA_E_ALIGN; } while (0)
+
+static inline bool pos(int a) { return a > 0; }
+static inline bool dtype_known(int d) { return elem_size(d) != 0; }
+
+extern "C" {
+
+int gfla_abi_version(void) { return GFLA_ABI_VERSION; }
+
+const char* gfla_error_string(int code) {
+    switch (code) {
+        case GFLA_OK: return "ok";
+        case GFLA_E_NULL: return "gfla: required pointer is NULL";
+        case GFLA_E_SHAPE: return "gfla: bad shape / kernel_size";
+        case GFLA_E_DTYPE: return "gfla: unsupported dtype combination";
+        case GFLA_E_ALIGN: return "gfla: misaligned pointer";
+        case GFLA_E_NOTSUP: return "gfla: requested algorithm cannot serve this call";
+        default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "gfla: unknown error";
+    }
+}
+
+int gfla_device_check(void) {
+    int dev = 0, major = 0, minor = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    return (major == 10 && minor == 0) ? GFLA_OK : static_cast<int>(cudaErrorNoKernelImageForDevice);
+}
+
+int gfla_block_extract_fwd(const void* source, const void* flow, void* out, int B, int C, int Hs, int Ws, int Hf,
+                           int Wf, int k, int dtype, int flow_dtype, gfla_stream_t stream) {
+    REQ_PTR(source); REQ_PTR(flow); REQ_PTR(out);
+    if (!pos(B) || !pos(C) || !pos(Hs) || !pos(Ws) || !pos(Hf) || !pos(Wf) || k < 1 || k > 9) return GFLA_E_SHAPE;
+    if (!dtype_known(dtype) || !flow_dtype_ok(dtype, flow_dtype)) return GFLA_E_DTYPE;
+    REQ_ALIGN(source, dtype); REQ_ALIGN(out, dtype); REQ_ALIGN(flow, flow_dtype);
+    return block_extract_fwd(source, flow, out, B, C, Hs, Ws, Hf, Wf, k, dtype, flow_dtype, (cudaStream_t)stream);
+}
+
+int gfla_block_extract_bwd(const void* source, const void* flow, const void* grad_out, void* grad_source,
+                           void* grad_flow, int B, int C, int Hs, int Ws, int Hf, int Wf, int k, int dtype,
+                           int flow_dtype, int accumulate, gfla_stream_t stream) {
+    REQ_PTR(source); REQ_PTR(flow); REQ_PTR(grad_out); REQ_PTR(grad_source); REQ_PTR(grad_flow);
+    if (!pos(B) || !pos(C) || !pos(Hs) || !pos(Ws) || !pos(Hf) || !pos(Wf) || k < 1 || k > 9) return GFLA_E_SHAPE;
+    if (!dtype_known(dtype) || !flow_dtype_ok(dtype, flow_dtype)) return GFLA_E_DTYPE;
+    REQ_ALIGN(source, dtype); REQ_ALIGN(grad_out, dtype); REQ_ALIGN(grad_source, dtype);
+    REQ_ALIGN(flow, flow_dtype); REQ_ALIGN(grad_flow, flow_dtype);
+    return block_extract_bwd(source, flow, grad_out, grad_source, grad_flow, B, C, Hs, Ws, Hf, Wf, k, dtype, flow_dtype,
+                             accumulate, (cudaStream_t)stream);
+}
+
+int gfla_attn_reshape_fwd(const void* in, void* out, int B, int H, int W, int k, int dtype, gfla_stream_t stream) {
+    REQ_PTR(in); REQ_PTR(out);
+    if (!pos(B) || !pos(H) || !pos(W) || k < 1 || k > 9) return GFLA_E_SHAPE;
+    if (!dtype_known(dtype)) return GFLA_E_DTYPE;
+    REQ_ALIGN(in, dtype); REQ_ALIGN(out, dtype);
+    return attn_reshape_fwd(in, out, B, H, W, k, dtype, (cudaStream_t)stream);
+}
+
+int gfla_attn_reshape_bwd(const void* grad_out, void* grad_in, int B, int H, int W, int k, int dtype, int accumulate,
+                          gfla_stream_t stream) {
+    REQ_PTR(grad_out); REQ_PTR(grad_in);
+    if (!pos(B) || !pos(H) || !pos(W) || k < 1 || k > 9) return GFLA_E_SHAPE;
+    if (!dtype_known(dtype)) return GFLA_E_DTYPE;
+    REQ_ALIGN(grad_out, dtype); REQ_ALIGN(grad_in, dtype);
+    return attn_reshape_bwd(grad_out, grad_in, B, H, W, k, dtype, accumulate, (cudaStream_t)stream);
+}
+
+int gfla_resample2d_fwd(const void* in1, const void* in2, void* out, int B, int C, int Hi, int Wi, int H, int W, int ks,
+                        int dilation, int dtype, gfla_stream_t stream) {
+    REQ_PTR(in1); REQ_PTR(in2); REQ_PTR(out);
+    if (!pos(B) || !pos(C) || !pos(Hi) || !pos(Wi) || !pos(H) || !pos(W) || ks < 2 || ks > 9 || dilation < 1) return GFLA_E_SHAPE;
+    if (dtype != GFLA_F32 && dtype != GFLA_F64) return GFLA_E_DTYPE;
+    REQ_ALIGN(in1, dtype); REQ_ALIGN(in2, dtype); REQ_ALIGN(out, dtype);
+    return resample2d_fwd(in1, in2, out, B, C, Hi, Wi, H, W, ks, dilation, dtype, (cudaStream_t)stream);
+}
+
+int gfla_resample2d_bwd(const void* in1, const void* in2, const void* grad_out, void* grad_in1, void* grad_in2, int B,
+                        int C, int Hi, int Wi, int H, int W, int ks, int dilation, int dtype, int accumulate,
+                        gfla_stream_t stream) {
+    REQ_PTR(in1); REQ_PTR(in2); REQ_PTR(grad_out); REQ_PTR(grad_in1); REQ_PTR(grad_in2);
+    if (!pos(B) || !pos(C) || !pos(Hi) || !pos(Wi) || !pos(H) || !pos(W) || ks < 2 || ks > 9 || dilation < 1) return GFLA_E_SHAPE;
+    if (dtype != GFLA_F32 && dtype != GFLA_F64) return GFLA_E_DTYPE;
+    REQ_ALIGN(in1, dtype); REQ_ALIGN(in2, dtype); REQ_ALIGN(grad_out, dtype); REQ_ALIGN(grad_in1, dtype); REQ_ALIGN(grad_in2, dtype);
+    return resample2d_bwd(in1, in2, grad_out, grad_in1, grad_in2, B, C, Hi, Wi, H, W, ks, dilation, dtype, accumulate,
+                          (cudaStream_t)stream);
+}
+
+int gfla_local_attn_fwd(const void* source, const void* flow, const void* logits, void* out, void* probs, int B, int C,
+                        int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, int algo, gfla_stream_t stream) {
+    REQ_PTR(source); REQ_PTR(flow); REQ_PTR(logits); REQ_PTR(out);
+    if (!pos(B) || !pos(C) || !pos(Hs) || !pos(Ws) || !pos(H) || !pos(W) || k < 1 || k > 9) return GFLA_E_SHAPE;
+    if (!dtype_known(dtype) || !flow_dtype_ok(dtype, flow_dtype)) return GFLA_E_DTYPE;
+    if (algo < 0 || algo > 2) return GFLA_E_NOTSUP;
+    REQ_ALIGN(source, dtype); REQ_ALIGN(logits, dtype); REQ_ALIGN(out, dtype); REQ_ALIGN(flow, flow_dtype);
+    if (probs) REQ_ALIGN(probs, dtype);
+    const bool tc_ok = local_attn_fwd_tc_supported(B, C, Hs, Ws, H, W, k, dtype, flow_dtype, source, out);
+    if (algo == 2 && !tc_ok) return GFLA_E_NOTSUP;
+    if (algo == 2 || (algo == 0 && tc_ok))
+        return local_attn_fwd_tc(source, flow, logits, out, probs, B, C, Hs, Ws, H, W, k, dtype, flow_dtype, (cudaStream_t)stream);
+    return local_attn_fwd_gather(source, flow, logits, out, probs, B, C, Hs, Ws, H, W, k, dtype, flow_dtype, (cudaStream_t)stream);
+}
+
+int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits, const void* grad_out,
+                        void* grad_source, void* grad_flow, void* grad_logits, int B, int C, int Hs, int Ws, int H, int W,
+                        int k, int dtype, int flow_dtype, int accumulate, int algo, gfla_stream_t stream) {
+    REQ_PTR(source); REQ_PTR(flow); REQ_PTR(logits); REQ_PTR(grad_out); REQ_PTR(grad_source); REQ_PTR(grad_flow); REQ_PTR(grad_logits);
+    if (!pos(B) || !pos(C) || !pos(Hs) || !pos(Ws) || !pos(H) || !pos(W) || k < 1 || k > 9) return GFLA_E_SHAPE;
+    if (!dtype_known(dtype) || !flow_dtype_ok(dtype, flow_dtype)) return GFLA_E_DTYPE;
+    if (algo < 0 || algo > 2) return GFLA_E_NOTSUP;
+    if (algo == 2) return GFLA_E_NOTSUP;  // no tile kernel for the backward yet
+    REQ_ALIGN(source, dtype); REQ_ALIGN(logits, dtype); REQ_ALIGN(grad_out, dtype); REQ_ALIGN(grad_source, dtype);
+    REQ_ALIGN(grad_logits, dtype); REQ_ALIGN(flow, flow_dtype); REQ_ALIGN(grad_flow, flow_dtype);
+    return local_attn_bwd_gather(source, flow, logits, grad_out, grad_source, grad_flow, grad_logits, B, C, Hs, Ws, H, W,
+                                 k, dtype, flow_dtype, accumulate, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+"""Fused local attention and a drop-in ``ExtractorAttn``.
+
+Reference: model/networks/base_function.py:790-818.  The module keeps the
+reference's constructor, attribute names and ``state_dict`` keys
+(``fully_connect_layer.{0,2}.{weight,bias}``) so reference checkpoints load
+unchanged; what changes is how ``forward`` runs:
+
+    reference                                   here
+    ---------                                   ----
+    block_source = extractor(source, flow)      same (needed as conv input)
+    block_target = extractor(target, 0)         same
+    attn = fc(cat(block_target, block_source))  conv -> act -> conv produce LOGITS;
+           ... ending in Softmax(dim=1)         the softmax is folded into the fused kernel
+    attn = reshape(attn, k)                     --
+    out  = avg_pool2d(attn * block_source,k,k)  LocalAttnFunction(source, flow, logits): one kernel,
+                                                never touches the [B,C,kH,kW] product again
+"""
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import functional as F_
+from .block_extractor import BlockExtractor
+from .local_attn_reshape import LocalAttnReshape
+
+
+class LocalAttnFunction(Function):
+    """(source [B,C,Hs,Ws], flow [B,2,H,W], logits [B,k*k,H,W]) -> out [B,C,H,W]
+
+    out = avg_pool2d(LocalAttnReshape(softmax(logits, 1)) * BlockExtractor(k)(source, flow), k, k)
+    """
+
+    @staticmethod
+    def forward(ctx, source, flow_field, logits, kernel_size, algo="auto"):
+        assert source.is_contiguous() and flow_field.is_contiguous() and logits.is_contiguous()
+        ctx.save_for_backward(source, flow_field, logits)
+        ctx.kernel_size = kernel_size
+        ctx.algo = algo
+        return F_.local_attn_fwd(source, flow_field, logits, kernel_size, algo=algo)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        source, flow_field, logits = ctx.saved_tensors
+        gs, gf, gl = F_.local_attn_bwd(source, flow_field, logits, grad_output, ctx.kernel_size)
+        return gs, gf, gl, None, None
+
+
+def local_attention(source, flow_field, logits, kernel_size, algo="auto"):
+    return LocalAttnFunction.apply(source.contiguous(), flow_field.contiguous(), logits.contiguous(), kernel_size, algo)
+
+
+class ExtractorAttn(nn.Module):
+    """Drop-in for base_function.py:790-818 (same ctor, same parameters)."""
+
+    def __init__(self, feature_nc, kernel_size=4, nonlinearity=nn.LeakyReLU(), softmax=None):
+        super(ExtractorAttn, self).__init__()
+        self.kernel_size = kernel_size
+        hidden_nc = 128
+        self.fused_softmax = softmax is not None           # reference: `softmax=True` -> nn.Softmax(dim=1)
+        softmax = nonlinearity if softmax is None else nn.Softmax(dim=1)
+
+        self.extractor = BlockExtractor(kernel_size=kernel_size)
+        self.reshape = LocalAttnReshape()
+        self.fully_connect_layer = nn.Sequential(
+            nn.Conv2d(2 * feature_nc, hidden_nc, kernel_size=kernel_size, stride=kernel_size, padding=0),
+            nonlinearity,
+            nn.Conv2d(hidden_nc, kernel_size * kernel_size, kernel_size=1, stride=1, padding=0),
+            softmax,)
+
+    def _logits(self, source, target, flow_field):
+        block_source = self.extractor(source, flow_field)
+        block_target = self.extractor(target, torch.zeros_like(flow_field))
+        x = torch.cat((block_target, block_source), 1)
+        for layer in list(self.fully_connect_layer)[:-1]:      # everything up to (not including) the softmax
+            x = layer(x)
+        return x, block_source
+
+    def forward(self, source, target, flow_field):
+        logits, block_source = self._logits(source, target, flow_field)
+        if self.fused_softmax:
+            return local_attention(source, flow_field, logits, self.kernel_size)
+        # softmax=None in the reference means "apply the nonlinearity instead": keep the literal composition
+        attn_param = self.reshape(self.fully_connect_layer[-1](logits), self.kernel_size)
+        return torch.nn.functional.avg_pool2d(attn_param * block_source, self.kernel_size, self.kernel_size)
+
+    def hook_attn_param(self, source, target, flow_field):
+        logits, block_source = self._logits(source, target, flow_field)
+        if self.fused_softmax:
+            result, probs = F_.local_attn_fwd(source.contiguous(), flow_field.contiguous(), logits.contiguous(),
+                                              self.kernel_size, return_probs=True)
+            return probs, result
+        attn_param_ = self.fully_connect_layer[-1](logits)
+        attn_param = self.reshape(attn_param_, self.kernel_size)
+        return attn_param_, torch.nn.functional.avg_pool2d(attn_param * block_source, self.kernel_size, self.kernel_size)

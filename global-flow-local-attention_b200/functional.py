@@ -1,0 +1,168 @@
+"""Thin torch-tensor front end of the C ABI: pointer / size / stream plumbing only.
+
+Every function here checks what the reference's autograd Functions check
+(contiguity asserts: block_extractor.py:9-10, local_attn_reshape.py:9,
+resample2d.py:10-11; `df == 2`: block_extractor.py:16; `ds == k*k`:
+local_attn_reshape.py:13; CPU tensors -> NotImplementedError:
+block_extractor.py:23-24, local_attn_reshape.py:20-21) and then hands raw
+device pointers to libgfla_warp.so on the caller's current stream.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.GFLA_F32, torch.float64: _lib.GFLA_F64,
+       torch.bfloat16: _lib.GFLA_BF16, torch.float16: _lib.GFLA_F16}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype} (float32/float64, or bfloat16/float16 storage)") from None
+
+
+def _need_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if not t.is_cuda:
+            # same behaviour as the reference ops: there is no CPU implementation
+            raise NotImplementedError("GFLA warp ops are CUDA-only (sm_100a); got a CPU tensor")
+    dev = ts[0].device
+    for t in ts:
+        if t.device != dev:
+            raise ValueError("all tensors must live on the same CUDA device")
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+# --------------------------------------------------------------------------- block_extractor
+def block_extract_fwd(source: torch.Tensor, flow: torch.Tensor, k: int) -> torch.Tensor:
+    assert source.is_contiguous() and flow.is_contiguous()
+    bs, ds, hs, ws = source.size()
+    bf, df, hf, wf = flow.size()
+    assert df == 2
+    _need_cuda(source, flow)
+    out = source.new_empty((bs, ds, k * hf, k * wf))   # fully written by the kernel: no zero fill needed
+    with torch.cuda.device_of(source):
+        _lib.check(_lib.lib().gfla_block_extract_fwd(_p(source), _p(flow), _p(out), bs, ds, hs, ws, hf, wf, k,
+                                                     _dt(source), _dt(flow), _stream(source)), "block_extract_fwd")
+    return out
+
+
+def block_extract_bwd(source, flow, grad_out, k, grad_source=None, grad_flow=None):
+    """Returns (grad_source, grad_flow).  If buffers are passed, gradients are ADDED
+    into them (reference contract, block_extractor.py:35-40)."""
+    assert source.is_contiguous() and flow.is_contiguous()
+    grad_out = grad_out.contiguous()
+    _need_cuda(source, flow, grad_out)
+    bs, ds, hs, ws = source.size()
+    _, _, hf, wf = flow.size()
+    accumulate = 1
+    if grad_source is None:
+        grad_source, grad_flow, accumulate = torch.empty_like(source), torch.empty_like(flow), 0
+    with torch.cuda.device_of(source):
+        _lib.check(_lib.lib().gfla_block_extract_bwd(_p(source), _p(flow), _p(grad_out), _p(grad_source), _p(grad_flow),
+                                                     bs, ds, hs, ws, hf, wf, k, _dt(source), _dt(flow), accumulate,
+                                                     _stream(source)), "block_extract_bwd")
+    return grad_source, grad_flow
+
+
+# --------------------------------------------------------------------------- local_attn_reshape
+def attn_reshape_fwd(inputs: torch.Tensor, k: int) -> torch.Tensor:
+    assert inputs.is_contiguous()
+    bs, ds, hs, ws = inputs.size()
+    assert ds == k * k
+    _need_cuda(inputs)
+    out = inputs.new_empty((bs, 1, k * hs, k * ws))
+    with torch.cuda.device_of(inputs):
+        _lib.check(_lib.lib().gfla_attn_reshape_fwd(_p(inputs), _p(out), bs, hs, ws, k, _dt(inputs), _stream(inputs)),
+                   "attn_reshape_fwd")
+    return out
+
+
+def attn_reshape_bwd(grad_out: torch.Tensor, k: int, grad_in=None) -> torch.Tensor:
+    grad_out = grad_out.contiguous()
+    _need_cuda(grad_out)
+    bs, _, ho, wo = grad_out.size()
+    hs, ws = ho // k, wo // k
+    accumulate = 1
+    if grad_in is None:
+        grad_in, accumulate = grad_out.new_empty((bs, k * k, hs, ws)), 0
+    with torch.cuda.device_of(grad_out):
+        _lib.check(_lib.lib().gfla_attn_reshape_bwd(_p(grad_out), _p(grad_in), bs, hs, ws, k, _dt(grad_out), accumulate,
+                                                    _stream(grad_out)), "attn_reshape_bwd")
+    return grad_in
+
+
+# --------------------------------------------------------------------------- resample2d
+def resample2d_fwd(input1: torch.Tensor, input2: torch.Tensor, kernel_size: int, dilation: int) -> torch.Tensor:
+    assert input1.is_contiguous() and input2.is_contiguous()
+    _need_cuda(input1, input2)
+    _, d, hi, wi = input1.size()
+    b, three, h, w = input2.size()
+    assert three == 3, "input2 must be [B,3,H,W] = (dx, dy, sigma) (resample2d.py:51-52)"
+    if input2.dtype != input1.dtype:
+        raise TypeError("resample2d: input1 and input2 must share a dtype (float32 or float64)")
+    out = input1.new_empty((b, d, h, w))
+    with torch.cuda.device_of(input1):
+        _lib.check(_lib.lib().gfla_resample2d_fwd(_p(input1), _p(input2), _p(out), b, d, hi, wi, h, w, kernel_size,
+                                                  dilation, _dt(input1), _stream(input1)), "resample2d_fwd")
+    return out
+
+
+def resample2d_bwd(input1, input2, grad_out, kernel_size, dilation, grad_input1=None, grad_input2=None):
+    assert input1.is_contiguous() and input2.is_contiguous()
+    grad_out = grad_out.contiguous()
+    _need_cuda(input1, input2, grad_out)
+    _, d, hi, wi = input1.size()
+    b, _, h, w = input2.size()
+    accumulate = 1
+    if grad_input1 is None:
+        grad_input1, grad_input2, accumulate = torch.empty_like(input1), torch.empty_like(input2), 0
+    with torch.cuda.device_of(input1):
+        _lib.check(_lib.lib().gfla_resample2d_bwd(_p(input1), _p(input2), _p(grad_out), _p(grad_input1), _p(grad_input2),
+                                                  b, d, hi, wi, h, w, kernel_size, dilation, _dt(input1), accumulate,
+                                                  _stream(input1)), "resample2d_bwd")
+    return grad_input1, grad_input2
+
+
+# --------------------------------------------------------------------------- fused local attention
+ALGO = {"auto": 0, "gather": 1, "tile": 2}
+
+
+def local_attn_fwd(source, flow, logits, k, return_probs=False, algo="auto"):
+    assert source.is_contiguous() and flow.is_contiguous() and logits.is_contiguous()
+    _need_cuda(source, flow, logits)
+    bs, ds, hs, ws = source.size()
+    bf, df, h, w = flow.size()
+    assert df == 2 and bf == bs
+    assert logits.shape == (bs, k * k, h, w) and logits.dtype == source.dtype
+    out = source.new_empty((bs, ds, h, w))
+    probs = torch.empty_like(logits) if return_probs else None
+    with torch.cuda.device_of(source):
+        _lib.check(_lib.lib().gfla_local_attn_fwd(_p(source), _p(flow), _p(logits), _p(out), _p(probs), bs, ds, hs, ws,
+                                                  h, w, k, _dt(source), _dt(flow), ALGO[algo], _stream(source)),
+                   "local_attn_fwd")
+    return (out, probs) if return_probs else out
+
+
+def local_attn_bwd(source, flow, logits, grad_out, k, algo="auto"):
+    assert source.is_contiguous() and flow.is_contiguous() and logits.is_contiguous()
+    grad_out = grad_out.contiguous()
+    _need_cuda(source, flow, logits, grad_out)
+    bs, ds, hs, ws = source.size()
+    _, _, h, w = flow.size()
+    gs, gf, gl = torch.empty_like(source), torch.empty_like(flow), torch.empty_like(logits)
+    with torch.cuda.device_of(source):
+        _lib.check(_lib.lib().gfla_local_attn_bwd(_p(source), _p(flow), _p(logits), _p(grad_out), _p(gs), _p(gf), _p(gl),
+                                                  bs, ds, hs, ws, h, w, k, _dt(source), _dt(flow), 0, ALGO[algo],
+                                                  _stream(source)), "local_attn_bwd")
+    return gs, gf, gl

@@ -1,0 +1,149 @@
+/*
+ * gfla_warp.h -- C ABI of the B200-native (sm_100a) GFLA warping library.
+ *
+ * This is the drop-in boundary for the warping hot path of
+ * RenYurui/Global-Flow-Local-Attention: the three custom extensions under
+ * model/networks/ (block_extractor, local_attn_reshape, resample2d_package)
+ * and the local-attention softmax-weighted gather they feed (ExtractorAttn,
+ * model/networks/base_function.py:790-818).  Each entry point names the
+ * reference interface (pybind function, file:line) it replaces.
+ *
+ * Conventions (all entry points)
+ *   - plain pointers + sizes only: no torch / ATen types cross this boundary.
+ *     Pointers are DEVICE pointers to contiguous NCHW tensors on the device
+ *     that owns `stream` (the caller's current device).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *     The reference launches on at::cuda::getCurrentCUDAStream()
+ *     (block_extractor_kernel.cu:197); callers pass that same stream.
+ *   - nothing is allocated, retained or synchronised inside the library; there
+ *     is no global mutable state (safe under one host thread per GPU).
+ *   - return value: 0 on success; a negative GFLA_E_* code for argument
+ *     errors (nothing was launched); a positive cudaError_t if a launch
+ *     failed.  (The reference returns the constant 1 and checks nothing,
+ *     block_extractor_cuda.cc:12; see INTEGRATION.md for the shim that maps
+ *     this back to the legacy `int` return.)
+ *   - dtype codes describe the element type of source / output / logits /
+ *     gradient tensors; `flow_dtype` that of the flow field and its gradient.
+ *     F32 and F64 mirror the reference's AT_DISPATCH_FLOATING_TYPES
+ *     (float, double only).  BF16 / F16 storage is an extension: arithmetic
+ *     is fp32, and the flow may stay fp32 (`flow_dtype` = GFLA_F32) so the tap
+ *     indices are bit-identical to the fp32 reference.
+ *   - every size is an `int` like in the reference, but products are formed
+ *     in 64 bits (the reference overflows `int n` above 2^31 elements,
+ *     block_extractor_kernel.cu:33,180).
+ *   - `accumulate` (backward entry points): 1 = reference semantics -- the
+ *     gradients are ADDED into caller-provided (normally zero-filled) buffers
+ *     (block_extractor.py:35-36, resample2d.py:32-33); 0 = the library
+ *     overwrites them (zero-filling internally where it scatters), so the
+ *     caller may pass uninitialised memory.
+ */
+#ifndef GFLA_WARP_H_
+#define GFLA_WARP_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GFLA_ABI_VERSION 1
+
+typedef void* gfla_stream_t; /* cudaStream_t */
+
+enum gfla_dtype { GFLA_F32 = 0, GFLA_F64 = 1, GFLA_BF16 = 2, GFLA_F16 = 3 };
+
+enum gfla_error {
+    GFLA_OK = 0,
+    GFLA_E_NULL = -1,     /* a required pointer is NULL                          */
+    GFLA_E_SHAPE = -2,    /* non-positive size, or kernel_size outside [1, 9]    */
+    GFLA_E_DTYPE = -3,    /* unknown dtype code / unsupported dtype combination  */
+    GFLA_E_ALIGN = -4,    /* pointer not aligned to its element size             */
+    GFLA_E_NOTSUP = -5    /* requested fast path cannot serve this call          */
+};
+
+int gfla_abi_version(void);
+/* static string for any code returned by this library (GFLA_E_* or cudaError_t) */
+const char* gfla_error_string(int code);
+/* compute capability the library was built for (100) and whether the running
+ * device can execute it; returns 0 when usable. */
+int gfla_device_check(void);
+
+/* ------------------------------------------------------------------------ *
+ * block_extractor
+ *   replaces block_extractor_cuda.forward(source, flow_field, output, k)
+ *            block_extractor_cuda.backward(source, flow_field, grad_output,
+ *                                          grad_source, grad_flow_field, k)
+ *   (block_extractor/block_extractor_cuda.cc:5-33, kernels
+ *    block_extractor_kernel.cu:20-85 and :89-170)
+ *   source [B,C,Hs,Ws], flow [B,2,Hf,Wf] (ch0 = x, ch1 = y, in pixels)
+ *   out / grad_out [B,C,k*Hf,k*Wf]; Hs,Ws may differ from Hf,Wf
+ *   (external_function.py:61-66).
+ * ------------------------------------------------------------------------ */
+int gfla_block_extract_fwd(const void* source, const void* flow, void* out,
+                           int B, int C, int Hs, int Ws, int Hf, int Wf, int k,
+                           int dtype, int flow_dtype, gfla_stream_t stream);
+int gfla_block_extract_bwd(const void* source, const void* flow, const void* grad_out,
+                           void* grad_source, void* grad_flow,
+                           int B, int C, int Hs, int Ws, int Hf, int Wf, int k,
+                           int dtype, int flow_dtype, int accumulate, gfla_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * local_attn_reshape  ([B,k*k,H,W] -> [B,1,k*H,k*W], depth-to-space)
+ *   replaces local_attn_reshape_cuda.forward(inputs, output, k)
+ *            local_attn_reshape_cuda.backward(inputs, grad_output, grad_inputs, k)
+ *   (local_attn_reshape/local_attn_reshape_cuda.cc:5-29, kernels
+ *    local_attn_reshape_kernel.cu:20-61 and :65-108; `inputs` is unused by
+ *    the reference backward and is not part of this signature)
+ * ------------------------------------------------------------------------ */
+int gfla_attn_reshape_fwd(const void* in, void* out, int B, int H, int W, int k,
+                          int dtype, gfla_stream_t stream);
+int gfla_attn_reshape_bwd(const void* grad_out, void* grad_in, int B, int H, int W, int k,
+                          int dtype, int accumulate, gfla_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * resample2d  (Gaussian-weighted ks x ks warp with dilation)
+ *   replaces resample2d_cuda.forward(input1, input2, output, ks, dilation)
+ *            resample2d_cuda.backward(input1, input2, gradOutput,
+ *                                     gradInput1, gradInput2, ks, dilation)
+ *   (resample2d_package/resample2d_cuda.cc:6-33, kernels
+ *    resample2d_kernel.cu:20-95, :98-202, :204-330)
+ *   in1 [B,C,Hi,Wi]; in2 [B,3,H,W] = (dx, dy, sigma) -- the sigma plane is
+ *   appended by the Python module (resample2d.py:51-52); out [B,C,H,W];
+ *   grad_in2 [B,3,H,W] (all three planes are written, like :328).
+ *   in2 / grad_in2 have the same dtype as in1 (F32 or F64 only).
+ * ------------------------------------------------------------------------ */
+int gfla_resample2d_fwd(const void* in1, const void* in2, void* out,
+                        int B, int C, int Hi, int Wi, int H, int W, int ks, int dilation,
+                        int dtype, gfla_stream_t stream);
+int gfla_resample2d_bwd(const void* in1, const void* in2, const void* grad_out,
+                        void* grad_in1, void* grad_in2,
+                        int B, int C, int Hi, int Wi, int H, int W, int ks, int dilation,
+                        int dtype, int accumulate, gfla_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * fused local attention = the tail of ExtractorAttn.forward
+ *   (base_function.py:804-810 with softmax=True, generator.py:112):
+ *     out = avg_pool2d( LocalAttnReshape(Softmax_dim1(logits)) *
+ *                       BlockExtractor(k)(source, flow), k, k )
+ *   computed without materialising the [B,C,k*H,k*W] block tensor.
+ *   source [B,C,Hs,Ws]; flow [B,2,H,W]; logits [B,k*k,H,W] (pre-softmax);
+ *   out [B,C,H,W]; probs (optional, may be NULL) [B,k*k,H,W] receives the
+ *   softmax, i.e. what hook_attn_param returns (base_function.py:812-818).
+ *   Backward: grad_source follows `accumulate`; grad_flow [B,2,H,W] and
+ *   grad_logits [B,k*k,H,W] likewise.
+ *   `algo`: 0 = automatic choice, 1 = CUDA-core gather kernel,
+ *           2 = tcgen05 tile kernel (GFLA_E_NOTSUP if it cannot serve the call).
+ * ------------------------------------------------------------------------ */
+int gfla_local_attn_fwd(const void* source, const void* flow, const void* logits,
+                        void* out, void* probs,
+                        int B, int C, int Hs, int Ws, int H, int W, int k,
+                        int dtype, int flow_dtype, int algo, gfla_stream_t stream);
+int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits,
+                        const void* grad_out,
+                        void* grad_source, void* grad_flow, void* grad_logits,
+                        int B, int C, int Hs, int Ws, int H, int W, int k,
+                        int dtype, int flow_dtype, int accumulate, int algo,
+                        gfla_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFLA_WARP_H_ */

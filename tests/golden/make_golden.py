@@ -115,30 +115,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "resample2d.npz"), **rs)
 
     # ------------------------------------------------------------------ ExtractorAttn tail (fused op)
-    class ExtractFn(torch.autograd.Function):            # mirrors block_extractor.py:5-42
-        @staticmethod
-        def forward(ctx, source, flow, k):
-            ctx.save_for_backward(source, flow)
-            ctx.k = k
-            return torch.from_numpy(R.block_extract_fwd(source.numpy(), flow.numpy(), k))
-
-        @staticmethod
-        def backward(ctx, g):
-            s, f = ctx.saved_tensors
-            gs, gf = R.block_extract_bwd(s.numpy(), f.numpy(), np.ascontiguousarray(g.numpy()), ctx.k)
-            return torch.from_numpy(gs), torch.from_numpy(gf), None
-
-    class ReshapeFn(torch.autograd.Function):            # mirrors local_attn_reshape.py:5-37
-        @staticmethod
-        def forward(ctx, x, k):
-            ctx.save_for_backward(x)
-            ctx.k = k
-            return torch.from_numpy(R.attn_reshape_fwd(x.numpy(), k))
-
-        @staticmethod
-        def backward(ctx, g):
-            (x,) = ctx.saved_tensors
-            return torch.from_numpy(R.attn_reshape_bwd(x.numpy(), np.ascontiguousarray(g.numpy()), ctx.k)), None
+    from oracle.ref_pipeline import local_attn_fwd_bwd
 
     la = {}
     cases = [
@@ -158,18 +135,10 @@ def main():
             flow = smooth_flow(rng, B, H, W, 4.0)
         flow = np.ascontiguousarray(flow.astype(dt))
         logits = (2.0 * rng.standard_normal((B, k * k, H, W))).astype(dt)
-        ts = torch.from_numpy(src).requires_grad_()
-        tf = torch.from_numpy(flow).requires_grad_()
-        tl = torch.from_numpy(logits).requires_grad_()
-        block = ExtractFn.apply(ts, tf, k)                          # base_function.py:805
-        probs = torch.softmax(tl, dim=1)                            # nn.Softmax(dim=1), base_function.py:795,803
-        attn = ReshapeFn.apply(probs, k)                            # :808
-        out = torch.nn.functional.avg_pool2d(attn * block, k, k)    # :809
-        g = rng.standard_normal(tuple(out.shape)).astype(dt)
-        out.backward(torch.from_numpy(g))
-        for key, v in dict(source=src, flow=flow, logits=logits, out=out.detach().numpy(), probs=probs.detach().numpy(),
-                           grad_out=g, grad_source=ts.grad.numpy(), grad_flow=tf.grad.numpy(),
-                           grad_logits=tl.grad.numpy(), k=np.int32(k)).items():
+        g = rng.standard_normal((B, C, H, W)).astype(dt)
+        out, probs, gs, gf, gl = local_attn_fwd_bwd(R, src, flow, logits, g, k)   # base_function.py:804-810
+        for key, v in dict(source=src, flow=flow, logits=logits, out=out, probs=probs, grad_out=g, grad_source=gs,
+                           grad_flow=gf, grad_logits=gl, k=np.int32(k)).items():
             la[f"{name}/{key}"] = v
     np.savez_compressed(os.path.join(OUT, "local_attn.npz"), **la)
 

@@ -1,0 +1,388 @@
+"""GPU (-m gpu): the CUDA library, called through the C ABI, against
+  (1) the committed golden vectors (produced by the reference's own kernel bodies),
+  (2) the CPU oracle on fresh seeded inputs,
+  (3) size-independent properties at BASELINE.json's full sizes.
+Tolerances (north_star): fp32 <= 1e-4, bf16 <= 1e-2; integer tap selection bit-identical,
+which the fp32/fp64 forward of block_extractor / local_attn_reshape / resample2d shows by
+being BIT-EXACT against the oracle (those kernels are built without FMA contraction)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def host(t):
+    return t.detach().float().cpu().numpy() if t.dtype in (torch.bfloat16, torch.float16) else t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def F_():
+    import gfla_b200
+    from gfla_b200 import _lib
+    _lib.check(_lib.lib().gfla_device_check(), "device check")
+    return gfla_b200.functional
+
+
+def tol(dt, f32, f64):
+    return f32 if dt == np.float32 else f64
+
+
+# ----------------------------------------------------------------------------- golden vectors
+@pytest.mark.parametrize("case", sorted(load_golden("block_extractor")))
+def test_block_extractor_golden(F_, case):
+    g = load_golden("block_extractor")[case]
+    k = int(g["k"])
+    out = F_.block_extract_fwd(cu(g["source"]), cu(g["flow"]), k)
+    assert np.array_equal(host(out), g["out"]), "forward must be bit-exact (same taps, same arithmetic)"
+    gs, gf = F_.block_extract_bwd(cu(g["source"]), cu(g["flow"]), cu(g["grad_out"]), k)
+    t = tol(g["source"].dtype, 1e-5, 1e-12)
+    np.testing.assert_allclose(host(gs), g["grad_source"], rtol=t, atol=t)
+    np.testing.assert_allclose(host(gf), g["grad_flow"], rtol=10 * t, atol=10 * t * max(1.0, np.abs(g["grad_flow"]).max()))
+
+
+@pytest.mark.parametrize("case", sorted(load_golden("local_attn_reshape")))
+def test_local_attn_reshape_golden(F_, case):
+    g = load_golden("local_attn_reshape")[case]
+    k = int(g["k"])
+    out = F_.attn_reshape_fwd(cu(g["in"]), k)
+    assert np.array_equal(host(out), g["out"])
+    if case == "layout":
+        assert np.array_equal(host(out)[0, 0, :3, :3], np.arange(9, dtype=np.float32).reshape(3, 3))
+    else:
+        assert np.array_equal(host(F_.attn_reshape_bwd(cu(g["grad_out"]), k)), g["grad_in"])
+
+
+@pytest.mark.parametrize("case", sorted(load_golden("resample2d")))
+def test_resample2d_golden(F_, case):
+    g = load_golden("resample2d")[case]
+    ks, dil = int(g["ks"]), int(g["dil"])
+    t = tol(g["in1"].dtype, 1e-6, 1e-14)     # exp() may differ in the last ulp between libm and CUDA
+    out = F_.resample2d_fwd(cu(g["in1"]), cu(g["in2"]), ks, dil)
+    np.testing.assert_allclose(host(out), g["out"], rtol=t, atol=t)
+    g1, g2 = F_.resample2d_bwd(cu(g["in1"]), cu(g["in2"]), cu(g["grad_out"]), ks, dil)
+    t = tol(g["in1"].dtype, 1e-5, 1e-12)
+    np.testing.assert_allclose(host(g1), g["grad_in1"], rtol=t, atol=t)
+    if case == "sigma0":
+        # degenerate SAFE_DIV(., 0) branch: the reference divides 0-weights by 1e-8; only finiteness
+        # and the forward are contractually meaningful here
+        assert np.isfinite(host(g2)).all() == np.isfinite(g["grad_in2"]).all()
+    else:
+        scale = max(1.0, np.abs(g["grad_in2"]).max())
+        np.testing.assert_allclose(host(g2), g["grad_in2"], rtol=1e-4 if g["in1"].dtype == np.float32 else 1e-10,
+                                   atol=(1e-4 if g["in1"].dtype == np.float32 else 1e-10) * scale)
+
+
+@pytest.mark.parametrize("algo", ["gather"])
+@pytest.mark.parametrize("case", sorted(load_golden("local_attn")))
+def test_local_attn_golden(F_, case, algo):
+    g = load_golden("local_attn")[case]
+    k = int(g["k"])
+    t = tol(g["source"].dtype, 1e-5, 1e-12)
+    s, f, l = cu(g["source"]), cu(g["flow"]), cu(g["logits"])
+    out, probs = F_.local_attn_fwd(s, f, l, k, return_probs=True, algo=algo)
+    np.testing.assert_allclose(host(probs), g["probs"], rtol=t, atol=t)
+    np.testing.assert_allclose(host(out), g["out"], rtol=t, atol=t)
+    gs, gf, gl = F_.local_attn_bwd(s, f, l, cu(g["grad_out"]), k)
+    np.testing.assert_allclose(host(gs), g["grad_source"], rtol=10 * t, atol=10 * t)
+    np.testing.assert_allclose(host(gf), g["grad_flow"], rtol=100 * t, atol=100 * t)
+    np.testing.assert_allclose(host(gl), g["grad_logits"], rtol=100 * t, atol=10 * t)
+
+
+# ----------------------------------------------------------------------------- vs the oracle, fresh inputs
+def _flow(rng, kind, B, H, W):
+    if kind == "iid":
+        return rng.uniform(-8, 8, (B, 2, H, W))
+    if kind == "border":
+        return rng.uniform(-1.5 * W, 1.5 * W, (B, 2, H, W))
+    if kind == "zero":
+        return np.zeros((B, 2, H, W))
+    if kind == "int":      # exactly integral displacements: frac == 0 everywhere
+        return rng.integers(-3, 4, (B, 2, H, W)).astype(np.float64)
+    coarse = torch.from_numpy(rng.uniform(-8, 8, (B, 2, max(H // 8, 2), max(W // 8, 2))))
+    return torch.nn.functional.interpolate(coarse, size=(H, W), mode="bilinear", align_corners=True).numpy()
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 7])
+@pytest.mark.parametrize("kind", ["iid", "border", "smooth", "int"])
+def test_block_extractor_vs_oracle(F_, oracle_lib, dt, k, kind):
+    rng = np.random.default_rng(k * 100 + len(kind))
+    B, C, Hs, Ws, H, W = 2, 5, 19, 23, 17, 21
+    s = rng.standard_normal((B, C, Hs, Ws)).astype(dt)
+    f = _flow(rng, kind, B, H, W).astype(dt)
+    out = F_.block_extract_fwd(cu(s), cu(f), k)
+    assert np.array_equal(host(out), oracle_lib.block_extract_fwd(s, f, k))
+    g = rng.standard_normal(out.shape).astype(dt)
+    gs, gf = F_.block_extract_bwd(cu(s), cu(f), cu(g), k)
+    ogs, ogf = oracle_lib.block_extract_bwd(s, f, g, k)
+    t = tol(dt, 2e-5, 1e-12)
+    np.testing.assert_allclose(host(gs), ogs, rtol=t, atol=t)
+    np.testing.assert_allclose(host(gf), ogf, rtol=t, atol=t * max(1.0, np.abs(ogf).max()))
+
+
+def test_block_extractor_accumulate_contract(F_, oracle_lib):
+    """legacy contract: backward ADDS into the caller's buffers (block_extractor.py:35-40)"""
+    rng = np.random.default_rng(5)
+    s = rng.standard_normal((1, 3, 9, 9)).astype(np.float32)
+    f = rng.uniform(-3, 3, (1, 2, 9, 9)).astype(np.float32)
+    g = rng.standard_normal((1, 3, 27, 27)).astype(np.float32)
+    gs0, gf0 = torch.full((1, 3, 9, 9), 2.0, device=DEV), torch.full((1, 2, 9, 9), -1.0, device=DEV)
+    F_.block_extract_bwd(cu(s), cu(f), cu(g), 3, gs0, gf0)
+    ogs, ogf = oracle_lib.block_extract_bwd(s, f, g, 3)
+    np.testing.assert_allclose(host(gs0), ogs + 2.0, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(host(gf0), ogf - 1.0, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("cfg", [(2, 1, 5.0), (4, 1, 2.0), (4, 2, 2.0), (6, 1, 3.0), (8, 1, 2.5)])
+def test_resample2d_vs_oracle(F_, oracle_lib, dt, cfg):
+    ks, dil, sigma = cfg
+    rng = np.random.default_rng(ks * 10 + dil)
+    B, C, Hi, Wi, H, W = 2, 6, 15, 18, 13, 16
+    a = rng.standard_normal((B, C, Hi, Wi)).astype(dt)
+    in2 = np.concatenate([rng.uniform(-6, 6, (B, 2, H, W)), np.full((B, 1, H, W), sigma)], 1).astype(dt)
+    out = F_.resample2d_fwd(cu(a), cu(in2), ks, dil)
+    t = tol(dt, 1e-6, 1e-14)
+    np.testing.assert_allclose(host(out), oracle_lib.resample2d_fwd(a, in2, ks, dil), rtol=t, atol=t)
+    g = rng.standard_normal(out.shape).astype(dt)
+    g1, g2 = F_.resample2d_bwd(cu(a), cu(in2), cu(g), ks, dil)
+    o1, o2 = oracle_lib.resample2d_bwd(a, in2, g, ks, dil)
+    t = tol(dt, 1e-5, 1e-12)
+    np.testing.assert_allclose(host(g1), o1, rtol=t, atol=t)
+    t = tol(dt, 1e-4, 1e-10)
+    np.testing.assert_allclose(host(g2), o2, rtol=t, atol=t * max(1.0, np.abs(o2).max()))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("kind", ["iid", "border", "smooth", "int", "zero"])
+def test_local_attn_vs_oracle(F_, oracle_lib, dt, k, kind):
+    rng = np.random.default_rng(k * 7 + len(kind))
+    B, C, H, W = 2, 6, 14, 17
+    s = rng.standard_normal((B, C, H, W)).astype(dt)
+    f = _flow(rng, kind, B, H, W).astype(dt)
+    l = (2 * rng.standard_normal((B, k * k, H, W))).astype(dt)
+    t = tol(dt, 1e-5, 1e-12)
+    out = F_.local_attn_fwd(cu(s), cu(f), cu(l), k, algo="gather")
+    np.testing.assert_allclose(host(out), oracle_lib.local_attn_fwd(s, f, l, k), rtol=t, atol=t)
+    g = rng.standard_normal(out.shape).astype(dt)
+    gs, gf, gl = F_.local_attn_bwd(cu(s), cu(f), cu(l), cu(g), k)
+    ogs, ogf, ogl = oracle_lib.local_attn_bwd(s, f, l, g, k)
+    np.testing.assert_allclose(host(gs), ogs, rtol=10 * t, atol=10 * t)
+    np.testing.assert_allclose(host(gf), ogf, rtol=100 * t, atol=100 * t)
+    np.testing.assert_allclose(host(gl), ogl, rtol=100 * t, atol=10 * t)
+
+
+@pytest.mark.parametrize("flow_dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("k", [3, 5])
+def test_local_attn_bf16_vs_oracle(F_, oracle_lib, k, flow_dt):
+    """bf16 storage: oracle = the fp32 reference arithmetic on the bf16-rounded inputs, tolerance 1e-2"""
+    torch.manual_seed(k)
+    B, C, H, W = 2, 32, 24, 20
+    s = torch.randn(B, C, H, W, device=DEV).bfloat16()
+    f = ((torch.rand(B, 2, H, W, device=DEV) * 12) - 6).to(flow_dt)
+    l = torch.randn(B, k * k, H, W, device=DEV).bfloat16()
+    out = F_.local_attn_fwd(s, f, l, k, algo="gather")
+    ref = oracle_lib.local_attn_fwd(host(s), host(f) if flow_dt != torch.float32 else f.cpu().numpy(), host(l), k)
+    np.testing.assert_allclose(host(out), ref, rtol=0, atol=1e-2)
+    g = torch.randn_like(out)
+    gs, gf, gl = F_.local_attn_bwd(s, f, l, g, k)
+    ogs, ogf, ogl = oracle_lib.local_attn_bwd(host(s), host(f) if flow_dt != torch.float32 else f.cpu().numpy(),
+                                              host(l), host(g), k)
+    np.testing.assert_allclose(host(gs), ogs, rtol=0, atol=1e-2)
+    np.testing.assert_allclose(host(gl), ogl, rtol=0, atol=1e-2)
+    np.testing.assert_allclose(host(gf), ogf, rtol=2e-2, atol=2e-2 * np.abs(ogf).max())
+
+
+# ----------------------------------------------------------------------------- autograd surface (reference tests)
+def test_gradcheck_block_extractor_double():
+    """model/networks/block_extractor/test_block_extractor.py:74-78"""
+    import gfla_b200
+    torch.manual_seed(0)
+    extractor = gfla_b200.BlockExtractor(3)
+    source = torch.rand(4, 6, 14, 10, dtype=torch.float64, device=DEV, requires_grad=True)
+    flow = (torch.rand(4, 2, 14, 10, dtype=torch.float64, device=DEV) * 1.8).requires_grad_()
+    assert torch.autograd.gradcheck(extractor, (source, flow), nondet_tol=1e-10)
+
+
+def test_gradcheck_local_attn_reshape_double():
+    """model/networks/local_attn_reshape/test_local_attn_reshape.py:66-70 (k = 3)"""
+    import gfla_b200
+    torch.manual_seed(0)
+    m = gfla_b200.LocalAttnReshape()
+    source = torch.rand(4, 9, 14, 10, dtype=torch.float64, device=DEV, requires_grad=True)
+    assert torch.autograd.gradcheck(lambda t: m(t, 3), (source,))
+
+
+def test_gradcheck_local_attention_double():
+    import gfla_b200
+    torch.manual_seed(1)
+    s = torch.rand(2, 3, 7, 6, dtype=torch.float64, device=DEV, requires_grad=True)
+    f = (torch.rand(2, 2, 7, 6, dtype=torch.float64, device=DEV) * 3.3 - 1.4).requires_grad_()
+    l = torch.randn(2, 9, 7, 6, dtype=torch.float64, device=DEV, requires_grad=True)
+    assert torch.autograd.gradcheck(lambda a, b, c: gfla_b200.local_attention(a, b, c, 3), (s, f, l), nondet_tol=1e-10)
+
+
+def test_resample2d_module_autograd(oracle_lib):
+    import gfla_b200
+    torch.manual_seed(2)
+    m = gfla_b200.Resample2d(4, 1, sigma=2)          # what PerceptualCorrectness uses, external_function.py:233
+    x = torch.randn(2, 5, 12, 12, device=DEV, requires_grad=True)
+    flow = (torch.rand(2, 2, 12, 12, device=DEV) * 4 - 2).requires_grad_()
+    out = m(x, flow)
+    g = torch.randn_like(out)
+    out.backward(g)
+    in2 = np.concatenate([host(flow), np.full((2, 1, 12, 12), 2.0, np.float32)], 1)
+    np.testing.assert_allclose(host(out), oracle_lib.resample2d_fwd(host(x), in2, 4, 1), rtol=1e-6, atol=1e-6)
+    o1, o2 = oracle_lib.resample2d_bwd(host(x), in2, host(g), 4, 1)
+    np.testing.assert_allclose(host(x.grad), o1, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(host(flow.grad), o2[:, :2], rtol=1e-4, atol=1e-4)   # sigma plane is dropped by cat
+
+
+def test_extractor_attn_module_matches_literal_composition():
+    """our ExtractorAttn (fused tail) == the reference's literal op sequence (base_function.py:804-810)
+    built from our own unfused ops + torch, same weights; forward, hook and all gradients."""
+    import gfla_b200
+    torch.manual_seed(3)
+    C, k, B, H, W = 8, 3, 2, 12, 10
+    m = gfla_b200.ExtractorAttn(C, k, softmax=True).to(DEV)
+    src = torch.randn(B, C, H, W, device=DEV, requires_grad=True)
+    tgt = torch.randn(B, C, H, W, device=DEV, requires_grad=True)
+    flow = (torch.rand(B, 2, H, W, device=DEV) * 6 - 3).requires_grad_()
+    out = m(src, tgt, flow)
+    g = torch.randn_like(out)
+    grads = torch.autograd.grad(out, (src, tgt, flow) + tuple(m.parameters()), g)
+
+    ex, rs = gfla_b200.BlockExtractor(k), gfla_b200.LocalAttnReshape()
+    bs = ex(src, flow)
+    bt = ex(tgt, torch.zeros_like(flow))
+    attn = m.fully_connect_layer(torch.cat((bt, bs), 1))            # includes the Softmax
+    ref = torch.nn.functional.avg_pool2d(rs(attn, k) * bs, k, k)
+    rgrads = torch.autograd.grad(ref, (src, tgt, flow) + tuple(m.parameters()), g)
+    np.testing.assert_allclose(host(out), host(ref), rtol=1e-5, atol=1e-5)
+    for a, b in zip(grads, rgrads):
+        np.testing.assert_allclose(host(a), host(b), rtol=2e-4, atol=2e-4 * max(1.0, float(b.abs().max())))
+    p, res = m.hook_attn_param(src, tgt, flow)
+    np.testing.assert_allclose(host(p), host(attn), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(host(res), host(ref), rtol=1e-5, atol=1e-5)
+
+
+def test_legacy_pybind_surface(oracle_lib):
+    """the reference's own wrapper logic (block_extractor.py:21-26: zero-filled output, then
+    `block_extractor_cuda.forward`) runs on the shim modules"""
+    import gfla_b200
+    gfla_b200.compat.install()
+    import block_extractor_cuda, local_attn_reshape_cuda, resample2d_cuda  # noqa: E401
+    rng = np.random.default_rng(11)
+    s = rng.standard_normal((1, 4, 10, 10)).astype(np.float32)
+    f = rng.uniform(-4, 4, (1, 2, 10, 10)).astype(np.float32)
+    ts, tf = cu(s), cu(f)
+    out = tf.new(1, 4, 30, 30).zero_()
+    assert block_extractor_cuda.forward(ts, tf, out, 3) == 1
+    assert np.array_equal(host(out), oracle_lib.block_extract_fwd(s, f, 3))
+    go = torch.randn_like(out)
+    gs, gf = ts.new(ts.size()).zero_(), tf.new(tf.size()).zero_()
+    assert block_extractor_cuda.backward(ts, tf, go, gs, gf, 3) == 1
+    ogs, ogf = oracle_lib.block_extract_bwd(s, f, host(go), 3)
+    np.testing.assert_allclose(host(gs), ogs, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(host(gf), ogf, rtol=1e-4, atol=1e-4)
+    x = torch.randn(1, 9, 5, 5, device=DEV)
+    o = x.new(1, 1, 15, 15).zero_()
+    assert local_attn_reshape_cuda.forward(x, o, 3) == 1
+    assert np.array_equal(host(o), oracle_lib.attn_reshape_fwd(host(x), 3))
+    in2 = torch.cat([tf, torch.full((1, 1, 10, 10), 5.0, device=DEV)], 1)
+    o2 = ts.new(1, 4, 10, 10).zero_()
+    assert resample2d_cuda.forward(ts, in2, o2, 2, 1) == 1
+    np.testing.assert_allclose(host(o2), oracle_lib.resample2d_fwd(s, host(in2), 2, 1), rtol=1e-6, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------- full-size properties (BASELINE cfg2 / cfg3)
+def _smooth_flow_t(B, H, W, amp=8.0, cell=16):
+    coarse = (torch.rand(B, 2, H // cell, W // cell, device=DEV) * 2 - 1) * amp
+    return torch.nn.functional.interpolate(coarse, size=(H, W), mode="bilinear", align_corners=True).contiguous()
+
+
+@pytest.mark.parametrize("algo", ["gather"])
+def test_cfg2_fused_equals_unfused_composition(F_, algo):
+    """B=2 slice of cfg2 (C=256, 256x256, k=5, bf16 data, fp32 flow): the fused kernel equals the
+    literal extractor -> softmax -> reshape -> mul -> avg_pool chain built from the (oracle-checked)
+    unfused kernels.  (The reference cannot run this shape at B=16 in one call: int overflow.)"""
+    torch.manual_seed(0)
+    B, C, H, W, k = 2, 256, 256, 256, 5
+    s = torch.randn(B, C, H, W, device=DEV).bfloat16()
+    f = _smooth_flow_t(B, H, W)
+    l = torch.randn(B, k * k, H, W, device=DEV).bfloat16()
+    out = F_.local_attn_fwd(s, f, l, k, algo=algo).float()
+    ref = torch.empty_like(out)
+    for b in range(B):      # block tensor of one sample: 256*1280*1280*4 B = 1.7 GB in fp32
+        blk = F_.block_extract_fwd(s[b:b + 1].float().contiguous(), f[b:b + 1].contiguous(), k)
+        attn = F_.attn_reshape_fwd(torch.softmax(l[b:b + 1].float(), 1).contiguous(), k)
+        ref[b:b + 1] = torch.nn.functional.avg_pool2d(attn * blk, k, k)
+        del blk, attn
+    err = (out - ref).abs().max().item()
+    assert err <= 1e-2, err
+    # property: one-hot attention at the centre tap with zero flow reproduces source / k^2
+    l1 = torch.full((1, k * k, H, W), -30000.0, device=DEV)
+    l1[:, (k * k) // 2] = 0
+    o1 = F_.local_attn_fwd(s[:1].contiguous(), torch.zeros(1, 2, H, W, device=DEV), l1.bfloat16(), k, algo=algo)
+    np.testing.assert_allclose(host(o1), host(s[:1]) / (k * k), rtol=0, atol=4e-3)
+
+
+def test_cfg2_linearity_in_source(F_):
+    """out is linear in source for fixed (flow, logits): f(a*s1 + s2) == a*f(s1) + f(s2) (fp32, full 256x256)"""
+    torch.manual_seed(1)
+    B, C, H, W, k = 1, 64, 256, 256, 5
+    s1, s2 = torch.randn(B, C, H, W, device=DEV), torch.randn(B, C, H, W, device=DEV)
+    f = (torch.rand(B, 2, H, W, device=DEV) * 16 - 8)
+    l = torch.randn(B, k * k, H, W, device=DEV)
+    o12 = F_.local_attn_fwd(0.5 * s1 + s2, f, l, k)
+    o = 0.5 * F_.local_attn_fwd(s1, f, l, k) + F_.local_attn_fwd(s2, f, l, k)
+    assert (o12 - o).abs().max().item() < 1e-5
+
+
+def test_cfg3_resample2d_properties(F_):
+    """cfg3-sized planes (512x512), reduced batch: (a) a constant image resamples to the same constant
+    for any flow (weights are normalised), (b) adjointness <resample(x), g> == <x, grad_in1(g)>."""
+    torch.manual_seed(2)
+    B, C, H, W = 2, 16, 512, 512
+    flow = torch.rand(B, 2, H, W, device=DEV) * 16 - 8
+    for ks, sigma in ((2, 5.0), (4, 2.0)):
+        in2 = torch.cat([flow, torch.full((B, 1, H, W), sigma, device=DEV)], 1).contiguous()
+        const = torch.full((B, C, H, W), 3.25, device=DEV)
+        out = F_.resample2d_fwd(const, in2, ks, 1)
+        assert (out - 3.25).abs().max().item() < 1e-5
+        x = torch.randn(B, C, H, W, device=DEV)
+        g = torch.randn(B, C, H, W, device=DEV)
+        # forward weights use floor(), grad_input1 uses int() for the fraction (reference quirk): restrict the
+        # adjoint identity to non-negative sample coordinates where the two agree
+        pos_flow = flow.abs()
+        in2p = torch.cat([pos_flow, torch.full((B, 1, H, W), sigma, device=DEV)], 1).contiguous()
+        y = F_.resample2d_fwd(x, in2p, ks, 1)
+        g1, _ = F_.resample2d_bwd(x, in2p, g, ks, 1)
+        lhs, rhs = (y.double() * g.double()).sum().item(), (x.double() * g1.double()).sum().item()
+        assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0) + 1.0, (lhs, rhs)
+
+
+def test_large_index_no_int_overflow(F_):
+    """output numel > 2^31 (the reference's `int n` overflows, block_extractor_kernel.cu:33,180):
+    B=1, C=64 bf16, 1024x1024 flow, k=6 -> 2.4e9 elements; spot-check against the small-shape kernel."""
+    torch.manual_seed(3)
+    C, H, W, k = 64, 1024, 1024, 6
+    s = torch.randn(1, C, H, W, device=DEV).bfloat16()
+    f = torch.rand(1, 2, H, W, device=DEV) * 8 - 4
+    out = F_.block_extract_fwd(s, f, k)
+    assert out.numel() > 2**31
+    # the last channel / bottom-right corner lives beyond the 2^31 boundary
+    y0, x0 = H - 16, W - 16
+    sub = F_.block_extract_fwd(s[:, -1:, :, :].contiguous(), f, k)
+    assert torch.equal(out[0, -1, y0 * k:, x0 * k:], sub[0, 0, y0 * k:, x0 * k:])
