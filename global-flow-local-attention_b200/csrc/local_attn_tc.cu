@@ -1,9 +1,452 @@
-// tcgen05 tile kernel for the fused local-attention forward (placeholder until
-// the tile kernel lands: reports "not supported" so the gather kernel serves
-// every call).
+// Fused local-attention FORWARD on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+//   out[b,c,p] = sum_t  Wfull[p,t] * source[b,c,t]
+//
+// Per output pixel p the reference's 4*k*k bilinear taps times softmax
+// probabilities (base_function.py:804-810, block_extractor_kernel.cu:57-82)
+// collapse to a (k+1)x(k+1) window of weights W_p.  Doing that weighted sum on
+// the CUDA cores costs >= (k+1)^2 = 36 multiply-adds AND shared-memory reads
+// per (pixel, channel): at cfg2 that is ~4x over the LSU/FMA budget of a
+// 70 %-of-HBM-roofline kernel.  So the sum is embedded in a dense GEMM:
+//
+//   * a group of 16x8 = 128 output pixels is the M dimension;
+//   * the channels (CN <= 256) are the N dimension;
+//   * K runs over the source positions of the group's tap footprint, one
+//     32-wide row segment at a time (K = 16 per tcgen05.mma, 2 MMAs per row);
+//   * B = the source rows themselves, TMA-loaded straight from NCHW as boxes
+//     [CN channels][32 x] with the 64-byte swizzle: that IS a K-major UMMA
+//     operand, no transposition;
+//   * A = the sparse weight matrix [128 pixels][32 positions] per row, built
+//     by 128 "builder" threads (one per pixel) from flow + logits;
+//   * D accumulates in TMEM ([128 lanes = pixels] x [CN fp32 columns]),
+//     double-buffered so the epilogue of group g overlaps the MMAs of g+1.
+//
+// The weight matrix is ~90 % zeros, i.e. the tensor pipe does ~12x redundant
+// work -- and is still several times faster than the CUDA cores would be,
+// which is what makes the kernel memory-bound again.
+//
+// Warp roles (10 warps, persistent CTA, static round-robin over groups):
+//   warp 0      producer: per group computes the tap bounding box from the flow,
+//               publishes it, issues the TMA row loads;
+//   warp 1      MMA issuer (one elected lane);
+//   warps 2-5   builders: softmax, tap/clamp arithmetic (bit-identical to the
+//               reference), window collapse, per-stage weight slabs;
+//   warps 6-9   epilogue: TMEM -> registers -> bf16 -> coalesced NCHW stores;
+//               pixels whose taps are not consecutive integers (fp32 rounding
+//               straddling an integer -- measure-zero) are recomputed here with
+//               the literal 4-tap path so indexing stays bit-identical.
+#include <climits>
+
 #include "common.cuh"
+#include "tc_common.cuh"
+
 namespace gfla {
-bool local_attn_fwd_tc_supported(int, int, int, int, int, int, int, int, int, const void*, const void*) { return false; }
-int local_attn_fwd_tc(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int,
-                      cudaStream_t) { return GFLA_E_NOTSUP; }
+
+namespace tc {
+
+constexpr int GW = 16, GH = 8;          // pixel group (M = 128)
+constexpr int BW = 32;                  // positions per row segment = 64-byte swizzle span in bf16
+constexpr int RCH = 2;                  // source rows per pipeline stage
+constexpr int NSTAGE = 4;
+constexpr int NINFO = 8;                // >= NSTAGE + 3 (producer run-ahead + 2 accumulators in flight)
+constexpr int NTHREADS = 320;
+constexpr int A_SLAB = 128 * 64;        // bytes: [128 pixels][32 positions] bf16, 64B rows, 64B swizzle
+
+struct GroupInfo { int x0, y0, ncb, nrc; };
+
+// softmax over the KK logits of one pixel (bf16 planes, stride hw), fp32 arithmetic
+template <int KK>
+__device__ __forceinline__ void pixel_softmax_f32(const __nv_bfloat16* __restrict__ lg, long long hw, float* p) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < KK; ++t) {
+        p[t] = __bfloat162float(lg[t * hw]);
+        mx = fmaxf(mx, p[t]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < KK; ++t) {
+        p[t] = expf(p[t] - mx);
+        sum += p[t];
+    }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int t = 0; t < KK; ++t) p[t] *= inv;
+}
+
+template <int CN>
+struct Smem {
+    static constexpr int S_SLAB = CN * 64;                   // [CN channels][32 x] bf16
+    static constexpr int S_STAGE = RCH * S_SLAB;
+    static constexpr int A_STAGE = RCH * A_SLAB;
+    static constexpr int OFF_S = 0;
+    static constexpr int OFF_A = OFF_S + NSTAGE * S_STAGE;
+    static constexpr int OFF_W = OFF_A + NSTAGE * A_STAGE;   // [36][128] bf16 collapsed windows
+    static constexpr int OFF_INFO = OFF_W + 36 * 128 * 2;
+    static constexpr int OFF_BAR = OFF_INFO + NINFO * 16;
+    static constexpr int NBAR = 3 * NSTAGE + 4 + NINFO;
+    static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+    static constexpr int TOTAL = OFF_TMEM + 16;
+    static constexpr int ALLOC = TOTAL + 1024;               // slack to align the base to 1024 B
+};
+
+// collapsed (K+1)x(K+1) window of one pixel, folded so that clamped (replicate-border) taps
+// land on in-bounds positions; live rows/cols are consecutive source positions starting at (Yb, Xb).
+template <int K>
+struct PixelWindow {
+    float w[(K + 1) * (K + 1)];
+    int Xb, Yb, s_lo, ncols, r_lo, nrows;
+    bool live;
+};
+
+template <int K>
+__device__ __forceinline__ bool taps_regular(float flow_x, float flow_y, int x, int y, int Hs, int Ws,
+                                             AxisTap<float> (&tx)[K], AxisTap<float> (&ty)[K]) {
+    bool regular = true;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        tx[j] = axis_tap<float>(flow_x, j - K / 2, x, Ws);
+        ty[j] = axis_tap<float>(flow_y, j - K / 2, y, Hs);
+        regular = regular && (tx[j].fl == tx[0].fl + j) && (ty[j].fl == ty[0].fl + j);
+    }
+    return regular;
+}
+
+template <int K, int CN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfloat16* __restrict__ src,
+                    const float* __restrict__ flow, const __nv_bfloat16* __restrict__ logits,
+                    __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ probs, int B, int C, int Hs, int Ws,
+                    int H, int W) {
+    using SM = Smem<CN>;
+    constexpr int K1 = K + 1, KK = K * K;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
+    uint64_t* full_s = bars;                      // [NSTAGE] TMA bytes landed
+    uint64_t* full_a = bars + NSTAGE;             // [NSTAGE] 128 builder arrivals
+    uint64_t* empty = bars + 2 * NSTAGE;          // [NSTAGE] MMAs of the stage retired
+    uint64_t* acc_full = bars + 3 * NSTAGE;       // [2]
+    uint64_t* acc_empty = bars + 3 * NSTAGE + 2;  // [2]
+    uint64_t* info_full = bars + 3 * NSTAGE + 4;  // [NINFO]
+    GroupInfo* infos = reinterpret_cast<GroupInfo*>(smem + SM::OFF_INFO);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_TMEM);
+    __nv_bfloat16* wsm = reinterpret_cast<__nv_bfloat16*>(smem + SM::OFF_W);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gxn = (W + GW - 1) / GW, gyn = (H + GH - 1) / GH;
+    const int ngroups = B * gyn * gxn;
+    const int c0 = blockIdx.y * CN;
+    const long long hw = (long long)H * W;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full_s[i], 1); mbar_init(&full_a[i], 128); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < NINFO; ++i) mbar_init(&info_full[i], 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmap_src);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * CN >= 32 ? 2 * CN : 32);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================= producer
+        uint32_t it = 0;  // global stage counter
+        int gi = 0;
+        for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
+            const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
+            int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m = lane + 32 * i, px = gx0 + (m & 15), py = gy0 + (m >> 4);
+                if (px < W && py < H) {
+                    const long long o = (long long)b * 2 * hw + (long long)py * W + px;
+                    const float fx = flow[o], fy = flow[o + hw];
+                    xmin = min(xmin, axis_tap<float>(fx, -(K / 2), px, Ws).lo);
+                    xmax = max(xmax, axis_tap<float>(fx, K - 1 - K / 2, px, Ws).hi);
+                    ymin = min(ymin, axis_tap<float>(fy, -(K / 2), py, Hs).lo);
+                    ymax = max(ymax, axis_tap<float>(fy, K - 1 - K / 2, py, Hs).hi);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+                xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+                ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+                ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+            }
+            const int ncb = (xmax - xmin + BW) / BW, nrc = (ymax - ymin + RCH) / RCH;
+            if (lane == 0) {
+                infos[gi % NINFO] = GroupInfo{xmin, ymin, ncb, nrc};
+                mbar_arrive(&info_full[gi % NINFO]);
+            }
+            for (int cb = 0; cb < ncb; ++cb)
+                for (int rc = 0; rc < nrc; ++rc, ++it) {
+                    const int slot = it % NSTAGE;
+                    mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&full_s[slot], SM::S_STAGE);
+#pragma unroll
+                        for (int rr = 0; rr < RCH; ++rr)
+                            tma_load_4d(smem + SM::OFF_S + slot * SM::S_STAGE + rr * SM::S_SLAB, &tmap_src, &full_s[slot],
+                                        xmin + cb * BW, ymin + rc * RCH + rr, c0, b);
+                    }
+                    __syncwarp();
+                }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer
+        constexpr uint32_t idesc = make_idesc_f16(128, CN, true, false, false);
+        uint32_t it = 0;
+        int gi = 0;
+        for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
+            mbar_wait(&info_full[gi % NINFO], (gi / NINFO) & 1);
+            const GroupInfo inf = infos[gi % NINFO];
+            const int nst = inf.ncb * inf.nrc, buf = gi & 1;
+            mbar_wait(&acc_empty[buf], ((gi >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * CN;
+            for (int st = 0; st < nst; ++st, ++it) {
+                const int slot = it % NSTAGE;
+                const uint32_t par = (it / NSTAGE) & 1;
+                mbar_wait(&full_s[slot], par);
+                mbar_wait(&full_a[slot], par);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a0 = smem_u32(smem + SM::OFF_A + slot * SM::A_STAGE);
+                    const uint32_t b0 = smem_u32(smem + SM::OFF_S + slot * SM::S_STAGE);
+#pragma unroll
+                    for (int rr = 0; rr < RCH; ++rr)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint64_t ad = make_smem_desc(a0 + rr * A_SLAB + h * 32, 16, 512, kSwizzle64);
+                            const uint64_t bd = make_smem_desc(b0 + rr * SM::S_SLAB + h * 32, 16, 512, kSwizzle64);
+                            umma_f16(d_tmem, ad, bd, idesc, (st | rr | h) != 0 ? 1u : 0u);
+                        }
+                    tc_commit(&empty[slot]);
+                    if (st == nst - 1) tc_commit(&acc_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < 6) {
+        // ================================================================= builders
+        const int q = warp & 3, m = q * 32 + lane;  // pixel index inside the group
+        const float inv_kk = 1.0f / static_cast<float>(KK);
+        uint32_t it = 0;
+        int gi = 0;
+        for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
+            const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
+            const int px = gx0 + (m & 15), py = gy0 + (m >> 4);
+            const bool valid = px < W && py < H;
+            int Xb = 0, Yb = 0, s_lo = 0, ncols = 0, r_lo = 0, nrows = 0;
+            bool live = false;
+            if (valid) {
+                const long long pofs = (long long)py * W + px;
+                float p[KK];
+                pixel_softmax_f32<KK>(logits + (long long)b * KK * hw + pofs, hw, p);
+                if (probs != nullptr && blockIdx.y == 0) {
+                    __nv_bfloat16* pr = probs + (long long)b * KK * hw + pofs;
+#pragma unroll
+                    for (int t = 0; t < KK; ++t) pr[t * hw] = __float2bfloat16_rn(p[t]);
+                }
+                const float fx = flow[(long long)b * 2 * hw + pofs], fy = flow[(long long)b * 2 * hw + hw + pofs];
+                AxisTap<float> tx[K], ty[K];
+                live = taps_regular<K>(fx, fy, px, py, Hs, Ws, tx, ty);
+                if (live) {
+                    float w[K1 * K1];
+#pragma unroll
+                    for (int i = 0; i < K1 * K1; ++i) w[i] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < K; ++i)
+#pragma unroll
+                        for (int j = 0; j < K; ++j) {
+                            const float pij = p[i * K + j] * inv_kk;
+                            w[i * K1 + j] += pij * (tx[j].wlo * ty[i].wlo);
+                            w[i * K1 + j + 1] += pij * (tx[j].whi * ty[i].wlo);
+                            w[(i + 1) * K1 + j] += pij * (tx[j].wlo * ty[i].whi);
+                            w[(i + 1) * K1 + j + 1] += pij * (tx[j].whi * ty[i].whi);
+                        }
+                    const int X0 = tx[0].fl, Y0 = ty[0].fl;
+                    // replicate border: fold weights of out-of-range columns / rows onto the border position
+#pragma unroll
+                    for (int r = 0; r < K1; ++r) {
+#pragma unroll
+                        for (int s = 0; s < K; ++s)
+                            if (X0 + s < 0) { w[r * K1 + s + 1] += w[r * K1 + s]; w[r * K1 + s] = 0.f; }
+#pragma unroll
+                        for (int s = K; s > 0; --s)
+                            if (X0 + s > Ws - 1) { w[r * K1 + s - 1] += w[r * K1 + s]; w[r * K1 + s] = 0.f; }
+                    }
+#pragma unroll
+                    for (int s = 0; s < K1; ++s) {
+#pragma unroll
+                        for (int r = 0; r < K; ++r)
+                            if (Y0 + r < 0) { w[(r + 1) * K1 + s] += w[r * K1 + s]; w[r * K1 + s] = 0.f; }
+#pragma unroll
+                        for (int r = K; r > 0; --r)
+                            if (Y0 + r > Hs - 1) { w[(r - 1) * K1 + s] += w[r * K1 + s]; w[r * K1 + s] = 0.f; }
+                    }
+                    s_lo = min(max(-X0, 0), K);
+                    const int s_hi = min(max(Ws - 1 - X0, 0), K);
+                    r_lo = min(max(-Y0, 0), K);
+                    const int r_hi = min(max(Hs - 1 - Y0, 0), K);
+                    ncols = s_hi - s_lo + 1;
+                    nrows = r_hi - r_lo + 1;
+                    Xb = clampi(X0 + s_lo, Ws - 1);
+                    Yb = clampi(Y0 + r_lo, Hs - 1);
+#pragma unroll
+                    for (int i = 0; i < K1 * K1; ++i) wsm[i * 128 + m] = __float2bfloat16_rn(w[i]);
+                }
+            }
+            mbar_wait(&info_full[gi % NINFO], (gi / NINFO) & 1);
+            const GroupInfo inf = infos[gi % NINFO];
+            for (int cb = 0; cb < inf.ncb; ++cb)
+                for (int rc = 0; rc < inf.nrc; ++rc, ++it) {
+                    const int slot = it % NSTAGE;
+                    mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1);
+                    uint8_t* a_stage = smem + SM::OFF_A + slot * SM::A_STAGE;
+                    const int C0 = inf.x0 + cb * BW, R0 = inf.y0 + rc * RCH;
+#pragma unroll
+                    for (int rr = 0; rr < RCH; ++rr) {
+                        uint8_t* row = a_stage + rr * A_SLAB + m * 64;
+                        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                        for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(row + ((ch ^ ((m >> 1) & 3)) << 4)) = z;
+                        if (live) {
+                            const int r = (R0 + rr) - Yb;  // index among the live rows
+                            if (r >= 0 && r < nrows) {
+                                const int e_lo = max(0, Xb - C0), e_hi = min(BW - 1, Xb + ncols - 1 - C0);
+                                for (int e = e_lo; e <= e_hi; ++e) {
+                                    const int s = s_lo + (e + C0 - Xb);
+                                    const __nv_bfloat16 wv = wsm[((r_lo + r) * K1 + s) * 128 + m];
+                                    *reinterpret_cast<__nv_bfloat16*>(row + ((((e >> 3) ^ ((m >> 1) & 3))) << 4) + (e & 7) * 2) = wv;
+                                }
+                            }
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    mbar_arrive(&full_a[slot]);
+                }
+        }
+    } else {
+        // ================================================================= epilogue
+        const int q = warp & 3, m = q * 32 + lane;
+        int gi = 0;
+        for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
+            const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
+            const int px = gx0 + (m & 15), py = gy0 + (m >> 4);
+            const bool valid = px < W && py < H;
+            const long long pofs = (long long)py * W + px;
+            bool regular = false;
+            float fx = 0.f, fy = 0.f;
+            if (valid) {
+                fx = flow[(long long)b * 2 * hw + pofs];
+                fy = flow[(long long)b * 2 * hw + hw + pofs];
+                AxisTap<float> tx[K], ty[K];
+                regular = taps_regular<K>(fx, fy, px, py, Hs, Ws, tx, ty);
+            }
+            const int buf = gi & 1;
+            mbar_wait(&acc_full[buf], (gi >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * CN;
+            __nv_bfloat16* o = out + ((long long)b * C + c0) * hw + pofs;
+#pragma unroll 1
+            for (int cc = 0; cc < CN / 32; ++cc) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + cc * 32, v);
+                tmem_ld_wait();
+                if (valid && regular) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[(long long)(cc * 32 + i) * hw] = __float2bfloat16_rn(__uint_as_float(v[i]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (valid && !regular) {
+                // literal 4-tap path (same arithmetic as the gather kernel's fall-back)
+                float p[KK];
+                pixel_softmax_f32<KK>(logits + (long long)b * KK * hw + pofs, hw, p);
+                const long long spl = (long long)Hs * Ws;
+                const __nv_bfloat16* s = src + ((long long)b * C + c0) * spl;
+                for (int c = 0; c < CN; ++c, s += spl) {
+                    float acc = 0.f;
+                    for (int i = 0; i < K; ++i) {
+                        const AxisTap<float> ty = axis_tap<float>(fy, i - K / 2, py, Hs);
+                        for (int j = 0; j < K; ++j) {
+                            const AxisTap<float> tx = axis_tap<float>(fx, j - K / 2, px, Ws);
+                            float v = 0.f;
+                            v += tx.wlo * ty.wlo * __bfloat162float(s[ty.lo * Ws + tx.lo]);
+                            v += tx.whi * ty.wlo * __bfloat162float(s[ty.lo * Ws + tx.hi]);
+                            v += tx.wlo * ty.whi * __bfloat162float(s[ty.hi * Ws + tx.lo]);
+                            v += tx.whi * ty.whi * __bfloat162float(s[ty.hi * Ws + tx.hi]);
+                            acc += p[i * K + j] * v;
+                        }
+                    }
+                    o[(long long)c * hw] = __float2bfloat16_rn(acc * (1.0f / static_cast<float>(KK)));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * CN >= 32 ? 2 * CN : 32);
+}
+
+template <int K, int CN>
+static int launch_tc(const void* src, const void* flow, const void* logits, void* out, void* probs, int B, int C, int Hs,
+                     int Ws, int H, int W, cudaStream_t st_) {
+    static const PFN_tmapEncodeTiled enc = tmap_encoder();
+    if (enc == nullptr) return GFLA_E_NOTSUP;
+    CUtensorMap tmap;
+    const cuuint64_t gdim[4] = {(cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)C, (cuuint64_t)B};
+    const cuuint64_t gstr[3] = {(cuuint64_t)Ws * 2, (cuuint64_t)Hs * Ws * 2, (cuuint64_t)C * Hs * Ws * 2};
+    const cuuint32_t box[4] = {BW, 1, CN, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return GFLA_E_NOTSUP;
+    auto kern = k_local_attn_fwd_tc<K, CN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<CN>::ALLOC);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const int ngroups = B * ((H + GH - 1) / GH) * ((W + GW - 1) / GW);
+    dim3 grid((unsigned)min(ngroups, sm_count()), (unsigned)(C / CN));
+    kern<<<grid, NTHREADS, Smem<CN>::ALLOC, st_>>>(tmap, (const __nv_bfloat16*)src, (const float*)flow,
+                                                   (const __nv_bfloat16*)logits, (__nv_bfloat16*)out,
+                                                   (__nv_bfloat16*)probs, B, C, Hs, Ws, H, W);
+    return launch_status();
+}
+
+}  // namespace tc
+
+static int pick_cn(int C) {
+    if (C % 256 == 0) return 256;
+    if (C == 128 || C == 64) return C;
+    return 0;
+}
+
+bool local_attn_fwd_tc_supported(int B, int C, int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype,
+                                 const void* src, const void* out) {
+    (void)B; (void)H; (void)W; (void)Hs; (void)out;
+    return dtype == GFLA_BF16 && flow_dtype == GFLA_F32 && (k == 3 || k == 5) && pick_cn(C) != 0 && (Ws % 8) == 0 &&
+           aligned(src, 16);
+}
+
+int local_attn_fwd_tc(const void* src, const void* flow, const void* logits, void* out, void* probs, int B, int C,
+                      int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, cudaStream_t st_) {
+    if (!local_attn_fwd_tc_supported(B, C, Hs, Ws, H, W, k, dtype, flow_dtype, src, out)) return GFLA_E_NOTSUP;
+    const int cn = pick_cn(C);
+#define GFLA_TC_CASE(K_, CN_) \
+    if (k == K_ && cn == CN_) return tc::launch_tc<K_, CN_>(src, flow, logits, out, probs, B, C, Hs, Ws, H, W, st_);
+    GFLA_TC_CASE(5, 256) GFLA_TC_CASE(5, 128) GFLA_TC_CASE(5, 64)
+    GFLA_TC_CASE(3, 256) GFLA_TC_CASE(3, 128) GFLA_TC_CASE(3, 64)
+#undef GFLA_TC_CASE
+    return GFLA_E_NOTSUP;
+}
+
 }  // namespace gfla
