@@ -12,6 +12,7 @@ int resample2d_bwd(const void*, const void*, const void*, void*, void*, int, int
 int local_attn_fwd_gather(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int local_attn_bwd_gather(const void*, const void*, const void*, const void*, void*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int local_attn_fwd_tc(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int tc_debug_set_buffer(void*);
 bool local_attn_fwd_tc_supported(int B, int C, int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, const void* src, const void* out);
 }  // namespace gfla
 
@@ -47,6 +48,8 @@ int gfla_device_check(void) {
     cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
     return (major == 10 && minor == 0) ? GFLA_OK : static_cast<int>(cudaErrorNoKernelImageForDevice);
 }
+
+int gfla_debug_set_buffer(void* host_mapped_u64x8) { return tc_debug_set_buffer(host_mapped_u64x8); }
 
 int gfla_block_extract_fwd(const void* source, const void* flow, void* out, int B, int C, int Hs, int Ws, int Hf,
                            int Wf, int k, int dtype, int flow_dtype, gfla_stream_t stream) {

@@ -12,11 +12,11 @@
 //   * a group of 16x8 = 128 output pixels is the M dimension;
 //   * the channels (CN <= 256) are the N dimension;
 //   * K runs over the source positions of the group's tap footprint, one
-//     32-wide row segment at a time (K = 16 per tcgen05.mma, 2 MMAs per row);
+//     16-wide row segment at a time (K = 16 = one tcgen05.mma per segment);
 //   * B = the source rows themselves, TMA-loaded straight from NCHW as boxes
-//     [CN channels][32 x] with the 64-byte swizzle: that IS a K-major UMMA
+//     [CN channels][16 x] with the 32-byte swizzle: that IS a K-major UMMA
 //     operand, no transposition;
-//   * A = the sparse weight matrix [128 pixels][32 positions] per row, built
+//   * A = the sparse weight matrix [128 pixels][16 positions] per segment, built
 //     by 128 "builder" threads (one per pixel) from flow + logits;
 //   * D accumulates in TMEM ([128 lanes = pixels] x [CN fp32 columns]),
 //     double-buffered so the epilogue of group g overlaps the MMAs of g+1.
@@ -45,12 +45,12 @@ namespace gfla {
 namespace tc {
 
 constexpr int GW = 16, GH = 8;          // pixel group (M = 128)
-constexpr int BW = 32;                  // positions per row segment = 64-byte swizzle span in bf16
+constexpr int BW = 16;                  // positions per row segment = 32-byte swizzle span in bf16 = K of one MMA
 constexpr int RCH = 2;                  // source rows per pipeline stage
-constexpr int NSTAGE = 4;
-constexpr int NINFO = 8;                // >= NSTAGE + 3 (producer run-ahead + 2 accumulators in flight)
+constexpr int NSTAGE = 8;
+constexpr int NINFO = 16;               // >= NSTAGE + 3 (producer run-ahead + 2 accumulators in flight)
 constexpr int NTHREADS = 320;
-constexpr int A_SLAB = 128 * 64;        // bytes: [128 pixels][32 positions] bf16, 64B rows, 64B swizzle
+constexpr int A_SLAB = 128 * 32;        // bytes: [128 pixels][16 positions] bf16, 32B rows, 32B swizzle
 
 struct GroupInfo { int x0, y0, ncb, nrc; };
 
@@ -76,7 +76,7 @@ __device__ __forceinline__ void pixel_softmax_f32(const __nv_bfloat16* __restric
 
 template <int CN>
 struct Smem {
-    static constexpr int S_SLAB = CN * 64;                   // [CN channels][32 x] bf16
+    static constexpr int S_SLAB = CN * 32;                   // [CN channels][16 x] bf16
     static constexpr int S_STAGE = RCH * S_SLAB;
     static constexpr int A_STAGE = RCH * A_SLAB;
     static constexpr int OFF_S = 0;
@@ -178,6 +178,8 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                 ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
                 ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
             }
+            // TMA needs the innermost start coordinate on a 16-byte boundary (8 bf16): align the box origin down
+            xmin &= ~7;
             const int ncb = (xmax - xmin + BW) / BW, nrc = (ymax - ymin + RCH) / RCH;
             if (lane == 0) {
                 infos[gi % NINFO] = GroupInfo{xmin, ymin, ncb, nrc};
@@ -186,7 +188,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             for (int cb = 0; cb < ncb; ++cb)
                 for (int rc = 0; rc < nrc; ++rc, ++it) {
                     const int slot = it % NSTAGE;
-                    mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1);
+                    mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x000200 | slot, it);
                     if (lane == 0) {
                         mbar_arrive_expect_tx(&full_s[slot], SM::S_STAGE);
 #pragma unroll
@@ -203,29 +205,27 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
         uint32_t it = 0;
         int gi = 0;
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
-            mbar_wait(&info_full[gi % NINFO], (gi / NINFO) & 1);
+            mbar_wait(&info_full[gi % NINFO], (gi / NINFO) & 1, 0x010500, gi);
             const GroupInfo inf = infos[gi % NINFO];
             const int nst = inf.ncb * inf.nrc, buf = gi & 1;
-            mbar_wait(&acc_empty[buf], ((gi >> 1) & 1) ^ 1);
+            mbar_wait(&acc_empty[buf], ((gi >> 1) & 1) ^ 1, 0x010400 | buf, gi);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * CN;
             for (int st = 0; st < nst; ++st, ++it) {
                 const int slot = it % NSTAGE;
                 const uint32_t par = (it / NSTAGE) & 1;
-                mbar_wait(&full_s[slot], par);
-                mbar_wait(&full_a[slot], par);
+                mbar_wait(&full_s[slot], par, 0x010000 | slot, it);
+                mbar_wait(&full_a[slot], par, 0x010100 | slot, it);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a0 = smem_u32(smem + SM::OFF_A + slot * SM::A_STAGE);
                     const uint32_t b0 = smem_u32(smem + SM::OFF_S + slot * SM::S_STAGE);
 #pragma unroll
-                    for (int rr = 0; rr < RCH; ++rr)
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const uint64_t ad = make_smem_desc(a0 + rr * A_SLAB + h * 32, 16, 512, kSwizzle64);
-                            const uint64_t bd = make_smem_desc(b0 + rr * SM::S_SLAB + h * 32, 16, 512, kSwizzle64);
-                            umma_f16(d_tmem, ad, bd, idesc, (st | rr | h) != 0 ? 1u : 0u);
-                        }
+                    for (int rr = 0; rr < RCH; ++rr) {
+                        const uint64_t ad = make_smem_desc(a0 + rr * A_SLAB, 16, 256, kSwizzle32);
+                        const uint64_t bd = make_smem_desc(b0 + rr * SM::S_SLAB, 16, 256, kSwizzle32);
+                        umma_f16(d_tmem, ad, bd, idesc, (st | rr) != 0 ? 1u : 0u);
+                    }
                     tc_commit(&empty[slot]);
                     if (st == nst - 1) tc_commit(&acc_full[buf]);
                 }
@@ -302,20 +302,20 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                     for (int i = 0; i < K1 * K1; ++i) wsm[i * 128 + m] = __float2bfloat16_rn(w[i]);
                 }
             }
-            mbar_wait(&info_full[gi % NINFO], (gi / NINFO) & 1);
+            mbar_wait(&info_full[gi % NINFO], (gi / NINFO) & 1, 0x020500, gi);
             const GroupInfo inf = infos[gi % NINFO];
             for (int cb = 0; cb < inf.ncb; ++cb)
                 for (int rc = 0; rc < inf.nrc; ++rc, ++it) {
                     const int slot = it % NSTAGE;
-                    mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1);
+                    mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x020200 | slot, it);
                     uint8_t* a_stage = smem + SM::OFF_A + slot * SM::A_STAGE;
                     const int C0 = inf.x0 + cb * BW, R0 = inf.y0 + rc * RCH;
 #pragma unroll
                     for (int rr = 0; rr < RCH; ++rr) {
-                        uint8_t* row = a_stage + rr * A_SLAB + m * 64;
+                        uint8_t* row = a_stage + rr * A_SLAB + m * 32;
                         const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-                        for (int ch = 0; ch < 4; ++ch) *reinterpret_cast<uint4*>(row + ((ch ^ ((m >> 1) & 3)) << 4)) = z;
+                        *reinterpret_cast<uint4*>(row) = z;
+                        *reinterpret_cast<uint4*>(row + 16) = z;
                         if (live) {
                             const int r = (R0 + rr) - Yb;  // index among the live rows
                             if (r >= 0 && r < nrows) {
@@ -323,7 +323,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                                 for (int e = e_lo; e <= e_hi; ++e) {
                                     const int s = s_lo + (e + C0 - Xb);
                                     const __nv_bfloat16 wv = wsm[((r_lo + r) * K1 + s) * 128 + m];
-                                    *reinterpret_cast<__nv_bfloat16*>(row + ((((e >> 3) ^ ((m >> 1) & 3))) << 4) + (e & 7) * 2) = wv;
+                                    *reinterpret_cast<__nv_bfloat16*>(row + ((((e >> 3) ^ ((m >> 2) & 1))) << 4) + (e & 7) * 2) = wv;
                                 }
                             }
                         }
@@ -350,7 +350,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                 regular = taps_regular<K>(fx, fy, px, py, Hs, Ws, tx, ty);
             }
             const int buf = gi & 1;
-            mbar_wait(&acc_full[buf], (gi >> 1) & 1);
+            mbar_wait(&acc_full[buf], (gi >> 1) & 1, 0x030300 | buf, gi);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * CN;
             __nv_bfloat16* o = out + ((long long)b * C + c0) * hw + pofs;
@@ -408,7 +408,7 @@ static int launch_tc(const void* src, const void* flow, const void* logits, void
     const cuuint32_t box[4] = {BW, 1, CN, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), gdim, gstr, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return GFLA_E_NOTSUP;
     auto kern = k_local_attn_fwd_tc<K, CN>;
@@ -423,6 +423,11 @@ static int launch_tc(const void* src, const void* flow, const void* logits, void
 }
 
 }  // namespace tc
+
+int tc_debug_set_buffer(void* host_mapped) {
+    unsigned long long* p = static_cast<unsigned long long*>(host_mapped);
+    return static_cast<int>(cudaMemcpyToSymbol(tc::g_tc_dbg, &p, sizeof(p)));
+}
 
 static int pick_cn(int C) {
     if (C % 256 == 0) return 256;

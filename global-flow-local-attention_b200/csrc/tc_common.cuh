@@ -33,12 +33,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Debug channel: a host-mapped (pinned) buffer of 8 x u64 set through gfla_debug_set_buffer(); survives a trap.
+static __device__ unsigned long long* g_tc_dbg = nullptr;
+
 // Bounded wait: a protocol bug must abort the kernel (trap -> launch error), never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// `tag` identifies the waiter (role << 16 | barrier kind << 8 | slot) in the debug buffer.
+__device__ __noinline__ void mbar_timeout(uint32_t tag, uint32_t parity, uint32_t iter) {
+    unsigned long long* d = g_tc_dbg;
+    if (d != nullptr) {
+        if (atomicCAS(d, 0ull, (unsigned long long)tag | (1ull << 63)) == 0ull) {
+            d[1] = parity; d[2] = iter; d[3] = blockIdx.x; d[4] = threadIdx.x;
+        }
+        __threadfence_system();
+    }
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0, uint32_t iter = 0) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 6000000000LL) __trap();  // ~3 s at 2 GHz
+        if (clock64() - t0 > 2000000000LL) mbar_timeout(tag, parity, iter);  // ~1 s
     }
 }
 

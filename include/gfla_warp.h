@@ -66,6 +66,12 @@ const char* gfla_error_string(int code);
  * device can execute it; returns 0 when usable. */
 int gfla_device_check(void);
 
+/* Debug aid for the tile kernels: `host_mapped_u64x8` is a DEVICE-visible pointer to 8
+ * zero-initialised uint64 in pinned host memory (or NULL to disable).  If a pipeline
+ * barrier inside a tile kernel ever times out, the kernel records which one there and
+ * traps instead of hanging the GPU.  Not used on the normal path. */
+int gfla_debug_set_buffer(void* host_mapped_u64x8);
+
 /* ------------------------------------------------------------------------ *
  * block_extractor
  *   replaces block_extractor_cuda.forward(source, flow_field, output, k)
