@@ -170,6 +170,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--flow", default="smooth", choices=["smooth", "iid"])
     ap.add_argument("--algo", default="auto", choices=["auto", "gather", "tile"])
+    ap.add_argument("--layout", default="nhwc", choices=["nhwc", "nchw"],
+                    help="storage of the [B,C,H,W] feature tensors: channels_last (default, the tile kernels' fast layout) or contiguous NCHW")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -180,7 +182,8 @@ def main():
     config = {"workload": f"cfg2: fused block_extractor+local_attn_reshape+softmax fwd+bwd, per-GPU B={B} C={C} "
                           f"{H}x{W} k={k}, bf16 data / fp32 flow ({args.flow} flow)",
               "per_gpu_batch": B, "global_batch": B * world, "C": C, "H": H, "W": W, "k": k,
-              "flow": args.flow, "sharding": f"batch x{world} (no data-path collective)",
+              "flow": args.flow, "layout": "channels_last (NHWC storage)" if args.layout == "nhwc" else "contiguous NCHW",
+              "sharding": f"batch x{world} (no data-path collective)",
               "l2": "inputs (>=1 GiB per step) exceed the 126 MB L2; no explicit flush"}
 
     # ------------------------------------------------------------------ reference arm
@@ -216,6 +219,9 @@ def main():
     steps, warmup = max(1, args.steps), max(3, args.warmup)
 
     src_h, flow_h, logits_h, gout_h = make_inputs(torch, dev, B, C, H, W, k, seed=1234 + rank, flow_kind=args.flow)
+    if args.layout == "nhwc":   # torch.channels_last: same logical [B,C,H,W] tensors, pixel-major storage
+        src_h = src_h.contiguous(memory_format=torch.channels_last)
+        gout_h = gout_h.contiguous(memory_format=torch.channels_last)
     src, flow, logits, gout = (t.to(dev) for t in (src_h, flow_h, logits_h, gout_h))
 
     def step(record=None):

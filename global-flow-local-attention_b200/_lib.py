@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgfla_warp.so")
 
 GFLA_F32, GFLA_F64, GFLA_BF16, GFLA_F16 = 0, 1, 2, 3
+GFLA_NCHW, GFLA_NHWC = 0, 1
 ABI_VERSION = 1
 
 _vp, _i = ctypes.c_void_p, ctypes.c_int
@@ -28,8 +29,8 @@ SIGNATURES = {
     "gfla_attn_reshape_bwd": [_vp, _vp] + [_i] * 6 + [_vp],
     "gfla_resample2d_fwd": [_vp] * 3 + [_i] * 9 + [_vp],
     "gfla_resample2d_bwd": [_vp] * 5 + [_i] * 10 + [_vp],
-    "gfla_local_attn_fwd": [_vp] * 5 + [_i] * 10 + [_vp],
-    "gfla_local_attn_bwd": [_vp] * 7 + [_i] * 11 + [_vp],
+    "gfla_local_attn_fwd": [_vp] * 5 + [_i] * 11 + [_vp],
+    "gfla_local_attn_bwd": [_vp] * 7 + [_i] * 12 + [_vp],
 }
 
 _lib = None

@@ -9,11 +9,11 @@ int attn_reshape_fwd(const void*, void*, int, int, int, int, int, cudaStream_t);
 int attn_reshape_bwd(const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int resample2d_fwd(const void*, const void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int resample2d_bwd(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
-int local_attn_fwd_gather(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
-int local_attn_bwd_gather(const void*, const void*, const void*, const void*, void*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
-int local_attn_fwd_tc(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int local_attn_fwd_gather(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int local_attn_bwd_gather(const void*, const void*, const void*, const void*, void*, void*, void*, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int local_attn_fwd_tc(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int tc_debug_set_buffer(void*);
-bool local_attn_fwd_tc_supported(int B, int C, int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, const void* src, const void* out);
+bool local_attn_fwd_tc_supported(int B, int C, int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, int layout, const void* src, const void* out);
 }  // namespace gfla
 
 using namespace gfla;
@@ -110,23 +110,26 @@ int gfla_resample2d_bwd(const void* in1, const void* in2, const void* grad_out, 
 }
 
 int gfla_local_attn_fwd(const void* source, const void* flow, const void* logits, void* out, void* probs, int B, int C,
-                        int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, int algo, gfla_stream_t stream) {
+                        int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, int layout, int algo,
+                        gfla_stream_t stream) {
     REQ_PTR(source); REQ_PTR(flow); REQ_PTR(logits); REQ_PTR(out);
+    if (layout != GFLA_NCHW && layout != GFLA_NHWC) return GFLA_E_SHAPE;
     if (!pos(B) || !pos(C) || !pos(Hs) || !pos(Ws) || !pos(H) || !pos(W) || k < 1 || k > 9) return GFLA_E_SHAPE;
     if (!dtype_known(dtype) || !flow_dtype_ok(dtype, flow_dtype)) return GFLA_E_DTYPE;
     if (algo < 0 || algo > 2) return GFLA_E_NOTSUP;
     REQ_ALIGN(source, dtype); REQ_ALIGN(logits, dtype); REQ_ALIGN(out, dtype); REQ_ALIGN(flow, flow_dtype);
     if (probs) REQ_ALIGN(probs, dtype);
-    const bool tc_ok = local_attn_fwd_tc_supported(B, C, Hs, Ws, H, W, k, dtype, flow_dtype, source, out);
+    const bool tc_ok = local_attn_fwd_tc_supported(B, C, Hs, Ws, H, W, k, dtype, flow_dtype, layout, source, out);
     if (algo == 2 && !tc_ok) return GFLA_E_NOTSUP;
     if (algo == 2 || (algo == 0 && tc_ok))
-        return local_attn_fwd_tc(source, flow, logits, out, probs, B, C, Hs, Ws, H, W, k, dtype, flow_dtype, (cudaStream_t)stream);
-    return local_attn_fwd_gather(source, flow, logits, out, probs, B, C, Hs, Ws, H, W, k, dtype, flow_dtype, (cudaStream_t)stream);
+        return local_attn_fwd_tc(source, flow, logits, out, probs, B, C, Hs, Ws, H, W, k, dtype, flow_dtype, layout, (cudaStream_t)stream);
+    return local_attn_fwd_gather(source, flow, logits, out, probs, B, C, Hs, Ws, H, W, k, dtype, flow_dtype, layout, (cudaStream_t)stream);
 }
 
 int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits, const void* grad_out,
                         void* grad_source, void* grad_flow, void* grad_logits, int B, int C, int Hs, int Ws, int H, int W,
-                        int k, int dtype, int flow_dtype, int accumulate, int algo, gfla_stream_t stream) {
+                        int k, int dtype, int flow_dtype, int layout, int accumulate, int algo, gfla_stream_t stream) {
+    if (layout != GFLA_NCHW && layout != GFLA_NHWC) return GFLA_E_SHAPE;
     REQ_PTR(source); REQ_PTR(flow); REQ_PTR(logits); REQ_PTR(grad_out); REQ_PTR(grad_source); REQ_PTR(grad_flow); REQ_PTR(grad_logits);
     if (!pos(B) || !pos(C) || !pos(Hs) || !pos(Ws) || !pos(H) || !pos(W) || k < 1 || k > 9) return GFLA_E_SHAPE;
     if (!dtype_known(dtype) || !flow_dtype_ok(dtype, flow_dtype)) return GFLA_E_DTYPE;
@@ -135,7 +138,7 @@ int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits
     REQ_ALIGN(source, dtype); REQ_ALIGN(logits, dtype); REQ_ALIGN(grad_out, dtype); REQ_ALIGN(grad_source, dtype);
     REQ_ALIGN(grad_logits, dtype); REQ_ALIGN(flow, flow_dtype); REQ_ALIGN(grad_flow, flow_dtype);
     return local_attn_bwd_gather(source, flow, logits, grad_out, grad_source, grad_flow, grad_logits, B, C, Hs, Ws, H, W,
-                                 k, dtype, flow_dtype, accumulate, (cudaStream_t)stream);
+                                 k, dtype, flow_dtype, accumulate, layout, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -56,7 +56,7 @@ template <typename T, typename TF, int K>  // K = 0: run-time k (literal path on
 __global__ void __launch_bounds__(128)
 k_local_attn_fwd(const T* __restrict__ src, const TF* __restrict__ flow, const T* __restrict__ logits,
                  T* __restrict__ out, T* __restrict__ probs, int B, int C, int Hs, int Ws, int H, int W, int k_rt,
-                 int c_per_slice) {
+                 int c_per_slice, int nhwc) {
     using A = typename Acc<T>::type;
     const int k = K ? K : k_rt, KK = k * k;
     const long long hw = (long long)H * W, total = (long long)B * hw;
@@ -75,8 +75,11 @@ k_local_attn_fwd(const T* __restrict__ src, const TF* __restrict__ flow, const T
     const A flow_y = static_cast<A>(ld(flow + (long long)b * 2 * hw + hw + pofs));
     const long long spl = (long long)Hs * Ws;
     const int c0 = blockIdx.y * c_per_slice, c1 = min(C, c0 + c_per_slice);
-    const T* s = src + ((long long)b * C + c0) * spl;
-    T* o = out + ((long long)b * C + c0) * hw + pofs;
+    // element strides (channel, position): NCHW planes or channels-last pixels
+    const long long sc = nhwc ? 1 : spl, oc = nhwc ? 1 : hw;
+    const int sp = nhwc ? C : 1;
+    const T* s = src + (long long)b * C * spl + c0 * sc;
+    T* o = out + (long long)b * C * hw + c0 * oc + pofs * (nhwc ? C : 1);
     const A inv_kk = static_cast<A>(1) / static_cast<A>(KK);
 
     bool regular = false;
@@ -108,10 +111,10 @@ k_local_attn_fwd(const T* __restrict__ src, const TF* __restrict__ flow, const T
             int cx[K1], cy[K1];
 #pragma unroll
             for (int r = 0; r < K1; ++r) {
-                cx[r] = clampi(tx[0].fl + r, Ws - 1);
-                cy[r] = clampi(ty[0].fl + r, Hs - 1) * Ws;
+                cx[r] = clampi(tx[0].fl + r, Ws - 1) * sp;
+                cy[r] = clampi(ty[0].fl + r, Hs - 1) * Ws * sp;
             }
-            for (int c = c0; c < c1; ++c, s += spl, o += hw) {
+            for (int c = c0; c < c1; ++c, s += sc, o += oc) {
                 A acc = static_cast<A>(0);
 #pragma unroll
                 for (int r = 0; r < K1; ++r)
@@ -122,17 +125,17 @@ k_local_attn_fwd(const T* __restrict__ src, const TF* __restrict__ flow, const T
         }
     }
     if (!regular) {
-        for (int c = c0; c < c1; ++c, s += spl, o += hw) {
+        for (int c = c0; c < c1; ++c, s += sc, o += oc) {
             A acc = static_cast<A>(0);
             for (int i = 0; i < k; ++i) {
                 const AxisTap<A> ty = axis_tap<A>(flow_y, i - k / 2, y, Hs);
                 for (int j = 0; j < k; ++j) {
                     const AxisTap<A> tx = axis_tap<A>(flow_x, j - k / 2, x, Ws);
                     A v = static_cast<A>(0);
-                    v += tx.wlo * ty.wlo * ld(s + ty.lo * Ws + tx.lo);
-                    v += tx.whi * ty.wlo * ld(s + ty.lo * Ws + tx.hi);
-                    v += tx.wlo * ty.whi * ld(s + ty.hi * Ws + tx.lo);
-                    v += tx.whi * ty.whi * ld(s + ty.hi * Ws + tx.hi);
+                    v += tx.wlo * ty.wlo * ld(s + (ty.lo * Ws + tx.lo) * sp);
+                    v += tx.whi * ty.wlo * ld(s + (ty.lo * Ws + tx.hi) * sp);
+                    v += tx.wlo * ty.whi * ld(s + (ty.hi * Ws + tx.lo) * sp);
+                    v += tx.whi * ty.whi * ld(s + (ty.hi * Ws + tx.hi) * sp);
                     acc += p[i * k + j] * v;
                 }
             }
@@ -154,7 +157,7 @@ template <typename T, typename TF, int K>
 __global__ void __launch_bounds__(128)
 k_local_attn_bwd(const T* __restrict__ src, const TF* __restrict__ flow, const T* __restrict__ logits,
                  const T* __restrict__ gout, T* __restrict__ gsrc, TF* __restrict__ gflow, T* __restrict__ glogits,
-                 int B, int C, int Hs, int Ws, int H, int W, int k_rt, int accumulate) {
+                 int B, int C, int Hs, int Ws, int H, int W, int k_rt, int accumulate, int nhwc) {
     using A = typename Acc<T>::type;
     const int k = K ? K : k_rt, KK = k * k;
     const long long hw = (long long)H * W, total = (long long)B * hw;
@@ -168,9 +171,11 @@ k_local_attn_bwd(const T* __restrict__ src, const TF* __restrict__ flow, const T
     const A flow_x = static_cast<A>(ld(flow + (long long)b * 2 * hw + pofs));
     const A flow_y = static_cast<A>(ld(flow + (long long)b * 2 * hw + hw + pofs));
     const long long spl = (long long)Hs * Ws;
+    const long long sc = nhwc ? 1 : spl, oc = nhwc ? 1 : hw;   // element strides per channel
+    const int sp = nhwc ? C : 1;                               // element stride per source position
     const T* s = src + (long long)b * C * spl;
     T* gs = gsrc + (long long)b * C * spl;
-    const T* go = gout + (long long)b * C * hw + pofs;
+    const T* go = gout + (long long)b * C * hw + pofs * (nhwc ? C : 1);
     const A inv_kk = static_cast<A>(1) / static_cast<A>(KK);
 
     A dp[K ? K * K : kMaxK * kMaxK];  // d loss / d p_t
@@ -204,10 +209,10 @@ k_local_attn_bwd(const T* __restrict__ src, const TF* __restrict__ flow, const T
             int cx[K1], cy[K1];
 #pragma unroll
             for (int r = 0; r < K1; ++r) {
-                cx[r] = clampi(tx[0].fl + r, Ws - 1);
-                cy[r] = clampi(ty[0].fl + r, Hs - 1) * Ws;
+                cx[r] = clampi(tx[0].fl + r, Ws - 1) * sp;
+                cy[r] = clampi(ty[0].fl + r, Hs - 1) * Ws * sp;
             }
-            for (int c = 0; c < C; ++c, s += spl, gs += spl, go += hw) {
+            for (int c = 0; c < C; ++c, s += sc, gs += sc, go += oc) {
                 const A g = ld(go);
 #pragma unroll
                 for (int r = 0; r < K1; ++r)
@@ -236,15 +241,16 @@ k_local_attn_bwd(const T* __restrict__ src, const TF* __restrict__ flow, const T
             const AxisTap<A> ty = axis_tap<A>(flow_y, i - k / 2, y, Hs);
             for (int j = 0; j < k; ++j) {
                 const AxisTap<A> tx = axis_tap<A>(flow_x, j - k / 2, x, Ws);
-                const int oLT = ty.lo * Ws + tx.lo, oRT = ty.lo * Ws + tx.hi, oLB = ty.hi * Ws + tx.lo, oRB = ty.hi * Ws + tx.hi;
+                const int oLT = (ty.lo * Ws + tx.lo) * sp, oRT = (ty.lo * Ws + tx.hi) * sp, oLB = (ty.hi * Ws + tx.lo) * sp,
+                          oRB = (ty.hi * Ws + tx.hi) * sp;
                 const A pij = p[i * k + j] * inv_kk;
                 A qLT = 0, qRT = 0, qLB = 0, qRB = 0;
-                const T* sc = s;
+                const T* sq = s;
                 T* gc = gs;
                 const T* goc = go;
-                for (int c = 0; c < C; ++c, sc += spl, gc += spl, goc += hw) {
+                for (int c = 0; c < C; ++c, sq += sc, gc += sc, goc += oc) {
                     const A g = ld(goc);
-                    qLT += g * ld(sc + oLT); qRT += g * ld(sc + oRT); qLB += g * ld(sc + oLB); qRB += g * ld(sc + oRB);
+                    qLT += g * ld(sq + oLT); qRT += g * ld(sq + oRT); qLB += g * ld(sq + oLB); qRB += g * ld(sq + oRB);
                     const A gp = g * pij;
                     red_add(gc + oLT, gp * (tx.wlo * ty.wlo));
                     red_add(gc + oRT, gp * (tx.whi * ty.wlo));
@@ -274,24 +280,24 @@ k_local_attn_bwd(const T* __restrict__ src, const TF* __restrict__ flow, const T
 
 template <typename T, typename TF, int K>
 static int la_launch_fwd(const void* src, const void* flow, const void* logits, void* out, void* probs, int B, int C,
-                         int Hs, int Ws, int H, int W, int k, cudaStream_t st_) {
+                         int Hs, int Ws, int H, int W, int k, int nhwc, cudaStream_t st_) {
     const long long total = (long long)B * H * W;
     const int threads = 128, slices0 = channel_splits(total, C, threads), cps = (C + slices0 - 1) / slices0;
     dim3 grid((unsigned)((total + threads - 1) / threads), (unsigned)((C + cps - 1) / cps));
     k_local_attn_fwd<T, TF, K><<<grid, threads, 0, st_>>>((const T*)src, (const TF*)flow, (const T*)logits, (T*)out,
-                                                         (T*)probs, B, C, Hs, Ws, H, W, k, cps);
+                                                         (T*)probs, B, C, Hs, Ws, H, W, k, cps, nhwc);
     return launch_status();
 }
 
 template <typename T, typename TF, int K>
 static int la_launch_bwd(const void* src, const void* flow, const void* logits, const void* gout, void* gsrc,
                          void* gflow, void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate,
-                         cudaStream_t st_) {
+                         int nhwc, cudaStream_t st_) {
     const long long total = (long long)B * H * W;
     const int threads = 128;
     k_local_attn_bwd<T, TF, K><<<(unsigned)((total + threads - 1) / threads), threads, 0, st_>>>(
         (const T*)src, (const TF*)flow, (const T*)logits, (const T*)gout, (T*)gsrc, (TF*)gflow, (T*)glogits, B, C, Hs,
-        Ws, H, W, k, accumulate);
+        Ws, H, W, k, accumulate, nhwc);
     return launch_status();
 }
 
@@ -306,31 +312,34 @@ static int la_launch_bwd(const void* src, const void* flow, const void* logits, 
 
 template <typename T, typename TF>
 static int la_fwd_k(const void* src, const void* flow, const void* logits, void* out, void* probs, int B, int C, int Hs,
-                    int Ws, int H, int W, int k, cudaStream_t st_) {
-    GFLA_K_DISPATCH(la_launch_fwd, src, flow, logits, out, probs, B, C, Hs, Ws, H, W, k, st_)
+                    int Ws, int H, int W, int k, int nhwc, cudaStream_t st_) {
+    GFLA_K_DISPATCH(la_launch_fwd, src, flow, logits, out, probs, B, C, Hs, Ws, H, W, k, nhwc, st_)
 }
 template <typename T, typename TF>
 static int la_bwd_k(const void* src, const void* flow, const void* logits, const void* gout, void* gsrc, void* gflow,
-                    void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate, cudaStream_t st_) {
-    GFLA_K_DISPATCH(la_launch_bwd, src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, k, accumulate, st_)
+                    void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate, int nhwc,
+                    cudaStream_t st_) {
+    GFLA_K_DISPATCH(la_launch_bwd, src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, k, accumulate, nhwc, st_)
 }
 
 int local_attn_fwd_gather(const void* src, const void* flow, const void* logits, void* out, void* probs, int B, int C,
-                          int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, cudaStream_t st_) {
+                          int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, int layout, cudaStream_t st_) {
+    const int nhwc = layout == GFLA_NHWC;
     return GFLA_DISPATCH_T(dtype, [&]() -> int {
-        if (flow_dtype == dtype) return la_fwd_k<T, T>(src, flow, logits, out, probs, B, C, Hs, Ws, H, W, k, st_);
-        return la_fwd_k<T, float>(src, flow, logits, out, probs, B, C, Hs, Ws, H, W, k, st_);
+        if (flow_dtype == dtype) return la_fwd_k<T, T>(src, flow, logits, out, probs, B, C, Hs, Ws, H, W, k, nhwc, st_);
+        return la_fwd_k<T, float>(src, flow, logits, out, probs, B, C, Hs, Ws, H, W, k, nhwc, st_);
     });
 }
 
 int local_attn_bwd_gather(const void* src, const void* flow, const void* logits, const void* gout, void* gsrc,
                           void* gflow, void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int dtype,
-                          int flow_dtype, int accumulate, cudaStream_t st_) {
+                          int flow_dtype, int accumulate, int layout, cudaStream_t st_) {
+    const int nhwc = layout == GFLA_NHWC;
     if (!accumulate) cudaMemsetAsync(gsrc, 0, (size_t)B * C * Hs * Ws * elem_size(dtype), st_);
     return GFLA_DISPATCH_T(dtype, [&]() -> int {
         if (flow_dtype == dtype)
-            return la_bwd_k<T, T>(src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, k, accumulate, st_);
-        return la_bwd_k<T, float>(src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, k, accumulate, st_);
+            return la_bwd_k<T, T>(src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, k, accumulate, nhwc, st_);
+        return la_bwd_k<T, float>(src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, k, accumulate, nhwc, st_);
     });
 }
 

@@ -112,7 +112,12 @@ __device__ __forceinline__ bool taps_regular(float flow_x, float flow_y, int x, 
     return regular;
 }
 
-template <int K, int CN>
+// NHWC = channels-last storage of source / out (logical shapes stay [B,C,H,W]): every source position is
+// 2*C contiguous bytes, so the TMA boxes [64 channels][16 x] are made of 128-byte runs (the NCHW variant has
+// to fetch 32-byte runs, one per channel, and needs its box origin aligned to 8 pixels), the box origin is
+// unconstrained in x, the smem tile is an MN-major (channel-contiguous) UMMA B operand, and the epilogue
+// stores 64 contiguous bytes per thread.
+template <int K, int CN, bool NHWC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfloat16* __restrict__ src,
                     const float* __restrict__ flow, const __nv_bfloat16* __restrict__ logits,
@@ -178,8 +183,8 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                 ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
                 ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
             }
-            // TMA needs the innermost start coordinate on a 16-byte boundary (8 bf16): align the box origin down
-            xmin &= ~7;
+            // TMA needs the innermost start coordinate on a 16-byte boundary: in NCHW that is x (8 bf16)
+            if (!NHWC) xmin &= ~7;
             const int ncb = (xmax - xmin + BW) / BW, nrc = (ymax - ymin + RCH) / RCH;
             if (lane == 0) {
                 infos[gi % NINFO] = GroupInfo{xmin, ymin, ncb, nrc};
@@ -192,16 +197,24 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                     if (lane == 0) {
                         mbar_arrive_expect_tx(&full_s[slot], SM::S_STAGE);
 #pragma unroll
-                        for (int rr = 0; rr < RCH; ++rr)
-                            tma_load_4d(smem + SM::OFF_S + slot * SM::S_STAGE + rr * SM::S_SLAB, &tmap_src, &full_s[slot],
-                                        xmin + cb * BW, ymin + rc * RCH + rr, c0, b);
+                        for (int rr = 0; rr < RCH; ++rr) {
+                            uint8_t* dst = smem + SM::OFF_S + slot * SM::S_STAGE + rr * SM::S_SLAB;
+                            if (NHWC) {  // [CN/64 channel groups][16 x][64 channels]: one 2 KB box per channel group
+#pragma unroll
+                                for (int cg = 0; cg < CN / 64; ++cg)
+                                    tma_load_4d(dst + cg * 2048, &tmap_src, &full_s[slot], c0 + cg * 64, xmin + cb * BW,
+                                                ymin + rc * RCH + rr, b);
+                            } else {     // [CN channels][16 x]
+                                tma_load_4d(dst, &tmap_src, &full_s[slot], xmin + cb * BW, ymin + rc * RCH + rr, c0, b);
+                            }
+                        }
                     }
                     __syncwarp();
                 }
         }
     } else if (warp == 1) {
         // ================================================================= MMA issuer
-        constexpr uint32_t idesc = make_idesc_f16(128, CN, true, false, false);
+        constexpr uint32_t idesc = make_idesc_f16(128, CN, true, false, NHWC);
         uint32_t it = 0;
         int gi = 0;
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
@@ -223,7 +236,10 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
 #pragma unroll
                     for (int rr = 0; rr < RCH; ++rr) {
                         const uint64_t ad = make_smem_desc(a0 + rr * A_SLAB, 16, 256, kSwizzle32);
-                        const uint64_t bd = make_smem_desc(b0 + rr * SM::S_SLAB, 16, 256, kSwizzle32);
+                        // NCHW: B = [CN rows][16 x], K-major, 32B swizzle.  NHWC: B = [16 x][64 ch] per channel group,
+                        // MN-major, 128B swizzle: LBO = next channel group (2 KB), SBO = next 8 positions (1 KB).
+                        const uint64_t bd = NHWC ? make_smem_desc(b0 + rr * SM::S_SLAB, 2048, 1024, kSwizzle128)
+                                                 : make_smem_desc(b0 + rr * SM::S_SLAB, 16, 256, kSwizzle32);
                         umma_f16(d_tmem, ad, bd, idesc, (st | rr) != 0 ? 1u : 0u);
                     }
                     tc_commit(&empty[slot]);
@@ -353,15 +369,30 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             mbar_wait(&acc_full[buf], (gi >> 1) & 1, 0x030300 | buf, gi);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * CN;
-            __nv_bfloat16* o = out + ((long long)b * C + c0) * hw + pofs;
+            __nv_bfloat16* o = NHWC ? out + ((long long)b * hw + pofs) * C + c0 : out + ((long long)b * C + c0) * hw + pofs;
 #pragma unroll 1
             for (int cc = 0; cc < CN / 32; ++cc) {
                 uint32_t v[32];
                 tmem_ld_32x32(taddr + cc * 32, v);
                 tmem_ld_wait();
                 if (valid && regular) {
+                    if (NHWC) {
+                        uint4* o4 = reinterpret_cast<uint4*>(o + cc * 32);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) o[(long long)(cc * 32 + i) * hw] = __float2bfloat16_rn(__uint_as_float(v[i]));
+                        for (int i = 0; i < 4; ++i) {
+                            uint4 pk;
+                            __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
+                            __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
+                            __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
+                            __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+                            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                            o4[i] = pk;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[(long long)(cc * 32 + i) * hw] = __float2bfloat16_rn(__uint_as_float(v[i]));
+                    }
                 }
             }
             tc_fence_before();
@@ -372,22 +403,24 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                 float p[KK];
                 pixel_softmax_f32<KK>(logits + (long long)b * KK * hw + pofs, hw, p);
                 const long long spl = (long long)Hs * Ws;
-                const __nv_bfloat16* s = src + ((long long)b * C + c0) * spl;
-                for (int c = 0; c < CN; ++c, s += spl) {
+                // element strides of source for (channel, position)
+                const long long sc = NHWC ? 1 : spl, sp = NHWC ? C : 1;
+                const __nv_bfloat16* s = NHWC ? src + (long long)b * spl * C + c0 : src + ((long long)b * C + c0) * spl;
+                for (int c = 0; c < CN; ++c, s += sc) {
                     float acc = 0.f;
                     for (int i = 0; i < K; ++i) {
                         const AxisTap<float> ty = axis_tap<float>(fy, i - K / 2, py, Hs);
                         for (int j = 0; j < K; ++j) {
                             const AxisTap<float> tx = axis_tap<float>(fx, j - K / 2, px, Ws);
                             float v = 0.f;
-                            v += tx.wlo * ty.wlo * __bfloat162float(s[ty.lo * Ws + tx.lo]);
-                            v += tx.whi * ty.wlo * __bfloat162float(s[ty.lo * Ws + tx.hi]);
-                            v += tx.wlo * ty.whi * __bfloat162float(s[ty.hi * Ws + tx.lo]);
-                            v += tx.whi * ty.whi * __bfloat162float(s[ty.hi * Ws + tx.hi]);
+                            v += tx.wlo * ty.wlo * __bfloat162float(s[(ty.lo * Ws + tx.lo) * sp]);
+                            v += tx.whi * ty.wlo * __bfloat162float(s[(ty.lo * Ws + tx.hi) * sp]);
+                            v += tx.wlo * ty.whi * __bfloat162float(s[(ty.hi * Ws + tx.lo) * sp]);
+                            v += tx.whi * ty.whi * __bfloat162float(s[(ty.hi * Ws + tx.hi) * sp]);
                             acc += p[i * K + j] * v;
                         }
                     }
-                    o[(long long)c * hw] = __float2bfloat16_rn(acc * (1.0f / static_cast<float>(KK)));
+                    o[NHWC ? (long long)c : (long long)c * hw] = __float2bfloat16_rn(acc * (1.0f / static_cast<float>(KK)));
                 }
             }
         }
@@ -397,21 +430,31 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
     if (warp == 1) tmem_dealloc(tmem_base, 2 * CN >= 32 ? 2 * CN : 32);
 }
 
-template <int K, int CN>
+template <int K, int CN, bool NHWC>
 static int launch_tc(const void* src, const void* flow, const void* logits, void* out, void* probs, int B, int C, int Hs,
                      int Ws, int H, int W, cudaStream_t st_) {
     static const PFN_tmapEncodeTiled enc = tmap_encoder();
     if (enc == nullptr) return GFLA_E_NOTSUP;
     CUtensorMap tmap;
-    const cuuint64_t gdim[4] = {(cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)C, (cuuint64_t)B};
-    const cuuint64_t gstr[3] = {(cuuint64_t)Ws * 2, (cuuint64_t)Hs * Ws * 2, (cuuint64_t)C * Hs * Ws * 2};
-    const cuuint32_t box[4] = {BW, 1, CN, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), gdim, gstr, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return GFLA_E_NOTSUP;
-    auto kern = k_local_attn_fwd_tc<K, CN>;
+    CUresult r;
+    if (NHWC) {  // (c, x, y, b), box [64 c][16 x]: 128-byte runs, 128B swizzle
+        const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)B};
+        const cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)Ws * C * 2, (cuuint64_t)Hs * Ws * C * 2};
+        const cuuint32_t box[4] = {64, BW, 1, 1};
+        r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), gdim, gstr, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {     // (x, y, c, b), box [CN c][16 x]: 32-byte runs, 32B swizzle
+        const cuuint64_t gdim[4] = {(cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)C, (cuuint64_t)B};
+        const cuuint64_t gstr[3] = {(cuuint64_t)Ws * 2, (cuuint64_t)Hs * Ws * 2, (cuuint64_t)C * Hs * Ws * 2};
+        const cuuint32_t box[4] = {BW, 1, CN, 1};
+        r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), gdim, gstr, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) return GFLA_E_NOTSUP;
+    auto kern = k_local_attn_fwd_tc<K, CN, NHWC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<CN>::ALLOC);
     if (e != cudaSuccess) return static_cast<int>(e);
     const int ngroups = B * ((H + GH - 1) / GH) * ((W + GW - 1) / GW);
@@ -436,18 +479,24 @@ static int pick_cn(int C) {
 }
 
 bool local_attn_fwd_tc_supported(int B, int C, int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype,
-                                 const void* src, const void* out) {
-    (void)B; (void)H; (void)W; (void)Hs; (void)out;
-    return dtype == GFLA_BF16 && flow_dtype == GFLA_F32 && (k == 3 || k == 5) && pick_cn(C) != 0 && (Ws % 8) == 0 &&
-           aligned(src, 16);
+                                 int layout, const void* src, const void* out) {
+    (void)B; (void)H; (void)W; (void)Hs;
+    if (!(dtype == GFLA_BF16 && flow_dtype == GFLA_F32 && (k == 3 || k == 5) && pick_cn(C) != 0 && aligned(src, 16)))
+        return false;
+    // NCHW: row pitch must be a multiple of 16 B for the tensor map; NHWC: pixel pitch 2*C always is, the
+    // epilogue's 16-byte stores need `out` aligned
+    return layout == GFLA_NHWC ? aligned(out, 16) : (Ws % 8) == 0;
 }
 
 int local_attn_fwd_tc(const void* src, const void* flow, const void* logits, void* out, void* probs, int B, int C,
-                      int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, cudaStream_t st_) {
-    if (!local_attn_fwd_tc_supported(B, C, Hs, Ws, H, W, k, dtype, flow_dtype, src, out)) return GFLA_E_NOTSUP;
+                      int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, int layout, cudaStream_t st_) {
+    if (!local_attn_fwd_tc_supported(B, C, Hs, Ws, H, W, k, dtype, flow_dtype, layout, src, out)) return GFLA_E_NOTSUP;
     const int cn = pick_cn(C);
-#define GFLA_TC_CASE(K_, CN_) \
-    if (k == K_ && cn == CN_) return tc::launch_tc<K_, CN_>(src, flow, logits, out, probs, B, C, Hs, Ws, H, W, st_);
+    const bool nhwc = layout == GFLA_NHWC;
+#define GFLA_TC_CASE(K_, CN_)                                                                                        \
+    if (k == K_ && cn == CN_)                                                                                        \
+        return nhwc ? tc::launch_tc<K_, CN_, true>(src, flow, logits, out, probs, B, C, Hs, Ws, H, W, st_)           \
+                    : tc::launch_tc<K_, CN_, false>(src, flow, logits, out, probs, B, C, Hs, Ws, H, W, st_);
     GFLA_TC_CASE(5, 256) GFLA_TC_CASE(5, 128) GFLA_TC_CASE(5, 64)
     GFLA_TC_CASE(3, 256) GFLA_TC_CASE(3, 128) GFLA_TC_CASE(3, 64)
 #undef GFLA_TC_CASE

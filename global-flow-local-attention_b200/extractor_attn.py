@@ -32,7 +32,7 @@ class LocalAttnFunction(Function):
 
     @staticmethod
     def forward(ctx, source, flow_field, logits, kernel_size, algo="auto"):
-        assert source.is_contiguous() and flow_field.is_contiguous() and logits.is_contiguous()
+        assert flow_field.is_contiguous() and logits.is_contiguous()
         ctx.save_for_backward(source, flow_field, logits)
         ctx.kernel_size = kernel_size
         ctx.algo = algo
@@ -45,8 +45,15 @@ class LocalAttnFunction(Function):
         return gs, gf, gl, None, None
 
 
+def _keep_format(t):
+    """contiguous NCHW stays, channels_last stays (the fast layout for the tile kernels); anything else -> NCHW"""
+    if t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)):
+        return t
+    return t.contiguous()
+
+
 def local_attention(source, flow_field, logits, kernel_size, algo="auto"):
-    return LocalAttnFunction.apply(source.contiguous(), flow_field.contiguous(), logits.contiguous(), kernel_size, algo)
+    return LocalAttnFunction.apply(_keep_format(source), flow_field.contiguous(), logits.contiguous(), kernel_size, algo)
 
 
 class ExtractorAttn(nn.Module):
@@ -86,7 +93,7 @@ class ExtractorAttn(nn.Module):
     def hook_attn_param(self, source, target, flow_field):
         logits, block_source = self._logits(source, target, flow_field)
         if self.fused_softmax:
-            result, probs = F_.local_attn_fwd(source.contiguous(), flow_field.contiguous(), logits.contiguous(),
+            result, probs = F_.local_attn_fwd(_keep_format(source), flow_field.contiguous(), logits.contiguous(),
                                               self.kernel_size, return_probs=True)
             return probs, result
         attn_param_ = self.fully_connect_layer[-1](logits)

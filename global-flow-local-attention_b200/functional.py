@@ -138,31 +138,49 @@ def resample2d_bwd(input1, input2, grad_out, kernel_size, dilation, grad_input1=
 ALGO = {"auto": 0, "gather": 1, "tile": 2}
 
 
+def _feature_layout(t: torch.Tensor) -> int:
+    """GFLA_NCHW for contiguous tensors, GFLA_NHWC for torch.channels_last ones (no copy either way)."""
+    if t.is_contiguous():
+        return _lib.GFLA_NCHW
+    if t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last):
+        return _lib.GFLA_NHWC
+    raise AssertionError("feature tensors must be contiguous (NCHW) or channels_last")
+
+
+def _like_layout(t: torch.Tensor, shape, layout: int) -> torch.Tensor:
+    fmt = torch.channels_last if layout == _lib.GFLA_NHWC else torch.contiguous_format
+    return torch.empty(shape, dtype=t.dtype, device=t.device, memory_format=fmt)
+
+
 def local_attn_fwd(source, flow, logits, k, return_probs=False, algo="auto"):
-    assert source.is_contiguous() and flow.is_contiguous() and logits.is_contiguous()
+    """source may be contiguous (NCHW) or channels_last; `out` comes back in the same memory format."""
+    layout = _feature_layout(source)
+    assert flow.is_contiguous() and logits.is_contiguous()
     _need_cuda(source, flow, logits)
     bs, ds, hs, ws = source.size()
     bf, df, h, w = flow.size()
     assert df == 2 and bf == bs
     assert logits.shape == (bs, k * k, h, w) and logits.dtype == source.dtype
-    out = source.new_empty((bs, ds, h, w))
+    out = _like_layout(source, (bs, ds, h, w), layout)
     probs = torch.empty_like(logits) if return_probs else None
     with torch.cuda.device_of(source):
         _lib.check(_lib.lib().gfla_local_attn_fwd(_p(source), _p(flow), _p(logits), _p(out), _p(probs), bs, ds, hs, ws,
-                                                  h, w, k, _dt(source), _dt(flow), ALGO[algo], _stream(source)),
+                                                  h, w, k, _dt(source), _dt(flow), layout, ALGO[algo], _stream(source)),
                    "local_attn_fwd")
     return (out, probs) if return_probs else out
 
 
 def local_attn_bwd(source, flow, logits, grad_out, k, algo="auto"):
-    assert source.is_contiguous() and flow.is_contiguous() and logits.is_contiguous()
-    grad_out = grad_out.contiguous()
+    layout = _feature_layout(source)
+    assert flow.is_contiguous() and logits.is_contiguous()
+    fmt = torch.channels_last if layout == _lib.GFLA_NHWC else torch.contiguous_format
+    grad_out = grad_out.contiguous(memory_format=fmt)
     _need_cuda(source, flow, logits, grad_out)
     bs, ds, hs, ws = source.size()
     _, _, h, w = flow.size()
-    gs, gf, gl = torch.empty_like(source), torch.empty_like(flow), torch.empty_like(logits)
+    gs, gf, gl = _like_layout(source, source.shape, layout), torch.empty_like(flow), torch.empty_like(logits)
     with torch.cuda.device_of(source):
         _lib.check(_lib.lib().gfla_local_attn_bwd(_p(source), _p(flow), _p(logits), _p(grad_out), _p(gs), _p(gf), _p(gl),
-                                                  bs, ds, hs, ws, h, w, k, _dt(source), _dt(flow), 0, ALGO[algo],
+                                                  bs, ds, hs, ws, h, w, k, _dt(source), _dt(flow), layout, 0, ALGO[algo],
                                                   _stream(source)), "local_attn_bwd")
     return gs, gf, gl

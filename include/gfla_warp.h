@@ -50,6 +50,10 @@ typedef void* gfla_stream_t; /* cudaStream_t */
 
 enum gfla_dtype { GFLA_F32 = 0, GFLA_F64 = 1, GFLA_BF16 = 2, GFLA_F16 = 3 };
 
+/* storage order of the [B,C,H,W] feature tensors of the fused op (source, out and their gradients);
+ * flow / logits / probs are always planar (NCHW).  NHWC = torch.channels_last. */
+enum gfla_layout { GFLA_NCHW = 0, GFLA_NHWC = 1 };
+
 enum gfla_error {
     GFLA_OK = 0,
     GFLA_E_NULL = -1,     /* a required pointer is NULL                          */
@@ -135,18 +139,20 @@ int gfla_resample2d_bwd(const void* in1, const void* in2, const void* grad_out,
  *   softmax, i.e. what hook_attn_param returns (base_function.py:812-818).
  *   Backward: grad_source follows `accumulate`; grad_flow [B,2,H,W] and
  *   grad_logits [B,k*k,H,W] likewise.
+ *   `layout`: GFLA_NCHW (the reference's contiguous layout) or GFLA_NHWC (channels-last: every
+ *           source position is 2*C contiguous bytes -- the layout the tile kernels are fastest on).
  *   `algo`: 0 = automatic choice, 1 = CUDA-core gather kernel,
  *           2 = tcgen05 tile kernel (GFLA_E_NOTSUP if it cannot serve the call).
  * ------------------------------------------------------------------------ */
 int gfla_local_attn_fwd(const void* source, const void* flow, const void* logits,
                         void* out, void* probs,
                         int B, int C, int Hs, int Ws, int H, int W, int k,
-                        int dtype, int flow_dtype, int algo, gfla_stream_t stream);
+                        int dtype, int flow_dtype, int layout, int algo, gfla_stream_t stream);
 int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits,
                         const void* grad_out,
                         void* grad_source, void* grad_flow, void* grad_logits,
                         int B, int C, int Hs, int Ws, int H, int W, int k,
-                        int dtype, int flow_dtype, int accumulate, int algo,
+                        int dtype, int flow_dtype, int layout, int accumulate, int algo,
                         gfla_stream_t stream);
 
 #ifdef __cplusplus

@@ -61,8 +61,10 @@ def test_argument_validation_needs_no_device(so):
     # misaligned pointer
     assert so.gfla_attn_reshape_fwd(p + 2, p, 1, 2, 2, 3, 0, None) == -4
     # unknown algo / tile kernel asked for a dtype it cannot serve
-    assert so.gfla_local_attn_fwd(p, p, p, p, None, 1, 1, 2, 2, 2, 2, 3, 0, 0, 9, None) == -5
-    assert so.gfla_local_attn_fwd(p, p, p, p, None, 1, 1, 2, 2, 2, 2, 3, 1, 1, 2, None) == -5
+    assert so.gfla_local_attn_fwd(p, p, p, p, None, 1, 1, 2, 2, 2, 2, 3, 0, 0, 0, 9, None) == -5
+    assert so.gfla_local_attn_fwd(p, p, p, p, None, 1, 1, 2, 2, 2, 2, 3, 1, 1, 0, 2, None) == -5
+    # unknown layout code
+    assert so.gfla_local_attn_fwd(p, p, p, p, None, 1, 1, 2, 2, 2, 2, 3, 0, 0, 5, 0, None) == -2
 
 
 def test_cpu_tensors_raise_like_the_reference():

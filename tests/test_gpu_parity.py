@@ -22,7 +22,8 @@ def cu(a, dtype=None):
 
 
 def host(t):
-    return t.detach().float().cpu().numpy() if t.dtype in (torch.bfloat16, torch.float16) else t.detach().cpu().numpy()
+    a = t.detach().float().cpu().numpy() if t.dtype in (torch.bfloat16, torch.float16) else t.detach().cpu().numpy()
+    return np.ascontiguousarray(a)      # channels_last tensors come back with NHWC strides
 
 
 @pytest.fixture(scope="module")
@@ -397,6 +398,7 @@ def _tile_inputs(B, C, Hs, Ws, H, W, k, kind, seed):
     return s, f, l
 
 
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
 @pytest.mark.parametrize("kind", ["smooth", "iid", "border", "zero", "int"])
 @pytest.mark.parametrize("shape", [
     (2, 64, 32, 32, 32, 32, 5),      # aligned
@@ -406,10 +408,13 @@ def _tile_inputs(B, C, Hs, Ws, H, W, k, kind, seed):
     (1, 64, 24, 32, 19, 27, 3),      # source larger than the flow field (external_function.py:61-66 usage)
     (1, 512, 16, 24, 16, 24, 5),     # two channel chunks of 256
 ])
-def test_local_attn_tile_vs_oracle(F_, oracle_lib, shape, kind):
+def test_local_attn_tile_vs_oracle(F_, oracle_lib, shape, kind, layout):
     B, C, Hs, Ws, H, W, k = shape
     s, f, l = _tile_inputs(B, C, Hs, Ws, H, W, k, kind, seed=sum(shape) + len(kind))
+    if layout == "nhwc":             # channels_last storage: same logical tensor, the tile kernel's fast layout
+        s = s.contiguous(memory_format=torch.channels_last)
     out, probs = F_.local_attn_fwd(s, f, l, k, return_probs=True, algo="tile")
+    assert out.is_contiguous(memory_format=torch.channels_last if layout == "nhwc" else torch.contiguous_format)
     ref, rprobs = oracle_lib.local_attn_fwd(host(s), f.cpu().numpy(), host(l), k, return_probs=True)
     np.testing.assert_allclose(host(probs), rprobs, rtol=0, atol=4e-3)
     np.testing.assert_allclose(host(out), ref, rtol=0, atol=1e-2)            # north_star tolerance
@@ -432,3 +437,24 @@ def test_local_attn_tile_rejects_what_it_cannot_serve(F_):
 
 def test_cfg2_tile_equals_unfused_composition(F_):
     test_cfg2_fused_equals_unfused_composition(F_, "tile")
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_local_attn_channels_last_gather_and_backward(F_, oracle_lib, dt):
+    """channels_last tensors through the CUDA-core kernels (forward and backward), any dtype"""
+    torch.manual_seed(5)
+    B, C, H, W, k = 2, 16, 13, 11, 3
+    s = torch.randn(B, C, H, W, device=DEV).to(dt).contiguous(memory_format=torch.channels_last)
+    f = torch.rand(B, 2, H, W, device=DEV) * 8 - 4
+    l = torch.randn(B, k * k, H, W, device=DEV).to(dt)
+    g = torch.randn(B, C, H, W, device=DEV).to(dt).contiguous(memory_format=torch.channels_last)
+    out = F_.local_attn_fwd(s, f if dt == torch.float32 else f, l, k, algo="gather")
+    gs, gf, gl = F_.local_attn_bwd(s, f, l, g, k)
+    assert gs.is_contiguous(memory_format=torch.channels_last)
+    tol_ = 1e-5 if dt == torch.float32 else 1e-2
+    ref = oracle_lib.local_attn_fwd(host(s), host(f), host(l), k)
+    ogs, ogf, ogl = oracle_lib.local_attn_bwd(host(s), host(f), host(l), host(g), k)
+    np.testing.assert_allclose(host(out), ref, rtol=tol_, atol=tol_)
+    np.testing.assert_allclose(host(gs), ogs, rtol=10 * tol_, atol=10 * tol_)
+    np.testing.assert_allclose(host(gl), ogl, rtol=10 * tol_, atol=10 * tol_)
+    np.testing.assert_allclose(host(gf), ogf, rtol=20 * tol_, atol=20 * tol_ * max(1.0, np.abs(ogf).max()))

@@ -12,6 +12,8 @@ def main():
     _lib.check(_lib.lib().gfla_debug_set_buffer(dbg.data_ptr()), "debug buffer")
     torch.manual_seed(0)
     s = torch.randn(B, C, H, W, device="cuda").bfloat16()
+    if os.environ.get("NHWC"):
+        s = s.contiguous(memory_format=torch.channels_last)
     f = (torch.rand(B, 2, H, W, device="cuda") * 8 - 4)
     l = torch.randn(B, k * k, H, W, device="cuda").bfloat16()
     ref = F_.local_attn_fwd(s, f, l, k, algo="gather").float()
