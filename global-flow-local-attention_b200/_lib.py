@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgfla_warp.so")
+LIB_PATH = os.environ.get("GFLA_LIB") or os.path.join(_HERE, "lib", "libgfla_warp.so")   # GFLA_LIB: A/B testing of builds
 
 GFLA_F32, GFLA_F64, GFLA_BF16, GFLA_F16 = 0, 1, 2, 3
 GFLA_NCHW, GFLA_NHWC = 0, 1

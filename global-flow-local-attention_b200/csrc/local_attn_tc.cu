@@ -36,6 +36,7 @@
 //               straddling an integer -- measure-zero) are recomputed here with
 //               the literal 4-tap path so indexing stays bit-identical.
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -90,15 +91,6 @@ struct Smem {
     static constexpr int ALLOC = TOTAL + 1024;               // slack to align the base to 1024 B
 };
 
-// collapsed (K+1)x(K+1) window of one pixel, folded so that clamped (replicate-border) taps
-// land on in-bounds positions; live rows/cols are consecutive source positions starting at (Yb, Xb).
-template <int K>
-struct PixelWindow {
-    float w[(K + 1) * (K + 1)];
-    int Xb, Yb, s_lo, ncols, r_lo, nrows;
-    bool live;
-};
-
 template <int K>
 __device__ __forceinline__ bool taps_regular(float flow_x, float flow_y, int x, int y, int Hs, int Ws,
                                              AxisTap<float> (&tx)[K], AxisTap<float> (&ty)[K]) {
@@ -122,7 +114,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfloat16* __restrict__ src,
                     const float* __restrict__ flow, const __nv_bfloat16* __restrict__ logits,
                     __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ probs, int B, int C, int Hs, int Ws,
-                    int H, int W) {
+                    int H, int W, int prefetch_mode) {
     using SM = Smem<CN>;
     constexpr int K1 = K + 1, KK = K * K;
     extern __shared__ uint8_t smem_raw[];
@@ -159,9 +151,8 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
 
     if (warp == 0) {
         // ================================================================= producer
-        uint32_t it = 0;  // global stage counter
-        int gi = 0;
-        for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
+        // bounding box (clamped tap positions) of one pixel group: warp-collective
+        auto group_bbox = [&](int g, int& x0, int& y0, int& x1, int& y1) {
             const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
             int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
 #pragma unroll
@@ -185,6 +176,39 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             }
             // TMA needs the innermost start coordinate on a 16-byte boundary: in NCHW that is x (8 bf16)
             if (!NHWC) xmin &= ~7;
+            x0 = xmin; y0 = ymin; x1 = xmax; y1 = ymax;
+        };
+        uint32_t it = 0;  // global stage counter
+        int gi = 0;
+        int nx0 = 0, ny0 = 0, nx1 = 0, ny1 = 0;
+        if ((int)blockIdx.x < ngroups) group_bbox(blockIdx.x, nx0, ny0, nx1, ny1);
+        for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
+            const int b = g / (gxn * gyn);
+            const int xmin = nx0, ymin = ny0, xmax = nx1, ymax = ny1;
+            // the next group of this CTA lies ~gridDim.x groups ahead in memory: nobody has touched its source
+            // rows yet, so pull them into L2 now -- a whole group of time before the TMA loads need them
+            const int gn = g + gridDim.x;
+            if (gn < ngroups) {
+                group_bbox(gn, nx0, ny0, nx1, ny1);
+                const int bn = gn / (gxn * gyn), prow = ny1 - ny0 + 1;
+                if ((prefetch_mode & 255) == 2 && NHWC && CN == C) {
+                    // channels-last, all channels in this CTA: a row segment of the box is one contiguous range
+                    const uint32_t bytes = static_cast<uint32_t>(nx1 - nx0 + 1) * C * 2;
+                    for (int r = lane; r < prow; r += 32)
+                        prefetch_l2_bulk(src + (((long long)bn * Hs + ny0 + r) * Ws + nx0) * C, bytes);
+                } else if ((prefetch_mode & 255) == 1) {
+                    const int pcb = (nx1 - nx0 + BW) / BW;
+                    for (int idx = lane; idx < pcb * prow; idx += 32) {
+                        const int cb = idx / prow, yy = ny0 + idx % prow;
+                        if (NHWC) {
+#pragma unroll
+                            for (int cg = 0; cg < CN / 64; ++cg) tma_prefetch_4d(&tmap_src, c0 + cg * 64, nx0 + cb * BW, yy, bn);
+                        } else {
+                            tma_prefetch_4d(&tmap_src, nx0 + cb * BW, yy, c0, bn);
+                        }
+                    }
+                }
+            }
             const int ncb = (xmax - xmin + BW) / BW, nrc = (ymax - ymin + RCH) / RCH;
             if (lane == 0) {
                 infos[gi % NINFO] = GroupInfo{xmin, ymin, ncb, nrc};
@@ -252,13 +276,16 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
         // ================================================================= builders
         const int q = warp & 3, m = q * 32 + lane;  // pixel index inside the group
         const float inv_kk = 1.0f / static_cast<float>(KK);
+        const uint32_t wsm_a = smem_u32(smem + SM::OFF_W) + m * 4;      // [18 words][128 pixels] packed bf16x2 rows
+        const uint32_t a_base = smem_u32(smem + SM::OFF_A) + m * 32;    // this pixel's 32-byte row in slab 0
+        const uint32_t swz = ((m >> 2) & 1) << 4;                        // 32B swizzle: 16B chunk ^= bit 2 of the row
         uint32_t it = 0;
         int gi = 0;
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
             const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
             const int px = gx0 + (m & 15), py = gy0 + (m >> 4);
             const bool valid = px < W && py < H;
-            int Xb = 0, Yb = 0, s_lo = 0, ncols = 0, r_lo = 0, nrows = 0;
+            int X0 = 0, Y0 = 0;
             bool live = false;
             if (valid) {
                 const long long pofs = (long long)py * W + px;
@@ -272,74 +299,93 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                 const float fx = flow[(long long)b * 2 * hw + pofs], fy = flow[(long long)b * 2 * hw + hw + pofs];
                 AxisTap<float> tx[K], ty[K];
                 live = taps_regular<K>(fx, fy, px, py, Hs, Ws, tx, ty);
+                X0 = tx[0].fl;
+                Y0 = ty[0].fl;
                 if (live) {
+                    // collapsed window, separably: rows of x-weights first, then the y-weights
                     float w[K1 * K1];
 #pragma unroll
                     for (int i = 0; i < K1 * K1; ++i) w[i] = 0.f;
 #pragma unroll
-                    for (int i = 0; i < K; ++i)
+                    for (int i = 0; i < K; ++i) {
+                        float rowx[K1];
+#pragma unroll
+                        for (int s2 = 0; s2 < K1; ++s2) rowx[s2] = 0.f;
 #pragma unroll
                         for (int j = 0; j < K; ++j) {
                             const float pij = p[i * K + j] * inv_kk;
-                            w[i * K1 + j] += pij * (tx[j].wlo * ty[i].wlo);
-                            w[i * K1 + j + 1] += pij * (tx[j].whi * ty[i].wlo);
-                            w[(i + 1) * K1 + j] += pij * (tx[j].wlo * ty[i].whi);
-                            w[(i + 1) * K1 + j + 1] += pij * (tx[j].whi * ty[i].whi);
+                            rowx[j] += pij * tx[j].wlo;
+                            rowx[j + 1] += pij * tx[j].whi;
                         }
-                    const int X0 = tx[0].fl, Y0 = ty[0].fl;
-                    // replicate border: fold weights of out-of-range columns / rows onto the border position
 #pragma unroll
-                    for (int r = 0; r < K1; ++r) {
-#pragma unroll
-                        for (int s = 0; s < K; ++s)
-                            if (X0 + s < 0) { w[r * K1 + s + 1] += w[r * K1 + s]; w[r * K1 + s] = 0.f; }
-#pragma unroll
-                        for (int s = K; s > 0; --s)
-                            if (X0 + s > Ws - 1) { w[r * K1 + s - 1] += w[r * K1 + s]; w[r * K1 + s] = 0.f; }
+                        for (int s2 = 0; s2 < K1; ++s2) {
+                            w[i * K1 + s2] += ty[i].wlo * rowx[s2];
+                            w[(i + 1) * K1 + s2] += ty[i].whi * rowx[s2];
+                        }
                     }
+                    // replicate border (only pixels whose window crosses the image edge): fold the weights of
+                    // out-of-range columns / rows onto the border position
+                    if (X0 < 0 || X0 + K > Ws - 1 || Y0 < 0 || Y0 + K > Hs - 1) {
 #pragma unroll
-                    for (int s = 0; s < K1; ++s) {
+                        for (int r = 0; r < K1; ++r) {
 #pragma unroll
-                        for (int r = 0; r < K; ++r)
-                            if (Y0 + r < 0) { w[(r + 1) * K1 + s] += w[r * K1 + s]; w[r * K1 + s] = 0.f; }
+                            for (int s2 = 0; s2 < K; ++s2)
+                                if (X0 + s2 < 0) { w[r * K1 + s2 + 1] += w[r * K1 + s2]; w[r * K1 + s2] = 0.f; }
 #pragma unroll
-                        for (int r = K; r > 0; --r)
-                            if (Y0 + r > Hs - 1) { w[(r - 1) * K1 + s] += w[r * K1 + s]; w[r * K1 + s] = 0.f; }
+                            for (int s2 = K; s2 > 0; --s2)
+                                if (X0 + s2 > Ws - 1) { w[r * K1 + s2 - 1] += w[r * K1 + s2]; w[r * K1 + s2] = 0.f; }
+                        }
+#pragma unroll
+                        for (int s2 = 0; s2 < K1; ++s2) {
+#pragma unroll
+                            for (int r = 0; r < K; ++r)
+                                if (Y0 + r < 0) { w[(r + 1) * K1 + s2] += w[r * K1 + s2]; w[r * K1 + s2] = 0.f; }
+#pragma unroll
+                            for (int r = K; r > 0; --r)
+                                if (Y0 + r > Hs - 1) { w[(r - 1) * K1 + s2] += w[r * K1 + s2]; w[r * K1 + s2] = 0.f; }
+                        }
                     }
-                    s_lo = min(max(-X0, 0), K);
-                    const int s_hi = min(max(Ws - 1 - X0, 0), K);
-                    r_lo = min(max(-Y0, 0), K);
-                    const int r_hi = min(max(Hs - 1 - Y0, 0), K);
-                    ncols = s_hi - s_lo + 1;
-                    nrows = r_hi - r_lo + 1;
-                    Xb = clampi(X0 + s_lo, Ws - 1);
-                    Yb = clampi(Y0 + r_lo, Hs - 1);
+                    // a window lying entirely outside the image has been folded onto its last (first) column /
+                    // row, which belongs on border position 0 (Ws-1, Hs-1): shift the origin accordingly so that
+                    // "window column s <-> source position X0 + s" holds for every non-zero weight
+                    X0 = min(max(X0, -K), Ws - 1);
+                    Y0 = min(max(Y0, -K), Hs - 1);
+                    // pack each window row as bf16x2 words (K1 = 6 -> 3 words, K1 = 4 -> 2 words)
 #pragma unroll
-                    for (int i = 0; i < K1 * K1; ++i) wsm[i * 128 + m] = __float2bfloat16_rn(w[i]);
+                    for (int r = 0; r < K1; ++r)
+#pragma unroll
+                        for (int wq = 0; wq < K1 / 2; ++wq) {
+                            const __nv_bfloat162 v2 = __floats2bfloat162_rn(w[r * K1 + 2 * wq], w[r * K1 + 2 * wq + 1]);
+                            sts32(wsm_a + (r * (K1 / 2) + wq) * 512, *reinterpret_cast<const uint32_t*>(&v2));
+                        }
                 }
             }
             mbar_wait(&info_full[gi % NINFO], (gi / NINFO) & 1, 0x020500, gi);
             const GroupInfo inf = infos[gi % NINFO];
-            for (int cb = 0; cb < inf.ncb; ++cb)
+            for (int cb = 0; cb < inf.ncb; ++cb) {
+                const int e0 = X0 - (inf.x0 + cb * BW);            // box position of window column 0
+                const bool cols_hit = live && e0 > -K1 && e0 < BW;
                 for (int rc = 0; rc < inf.nrc; ++rc, ++it) {
                     const int slot = it % NSTAGE;
                     mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x020200 | slot, it);
-                    uint8_t* a_stage = smem + SM::OFF_A + slot * SM::A_STAGE;
-                    const int C0 = inf.x0 + cb * BW, R0 = inf.y0 + rc * RCH;
+                    const uint32_t a_stage = a_base + slot * SM::A_STAGE;
+                    const int R0 = inf.y0 + rc * RCH;
 #pragma unroll
                     for (int rr = 0; rr < RCH; ++rr) {
-                        uint8_t* row = a_stage + rr * A_SLAB + m * 32;
-                        const uint4 z = make_uint4(0, 0, 0, 0);
-                        *reinterpret_cast<uint4*>(row) = z;
-                        *reinterpret_cast<uint4*>(row + 16) = z;
-                        if (live) {
-                            const int r = (R0 + rr) - Yb;  // index among the live rows
-                            if (r >= 0 && r < nrows) {
-                                const int e_lo = max(0, Xb - C0), e_hi = min(BW - 1, Xb + ncols - 1 - C0);
-                                for (int e = e_lo; e <= e_hi; ++e) {
-                                    const int s = s_lo + (e + C0 - Xb);
-                                    const __nv_bfloat16 wv = wsm[((r_lo + r) * K1 + s) * 128 + m];
-                                    *reinterpret_cast<__nv_bfloat16*>(row + ((((e >> 3) ^ ((m >> 2) & 1))) << 4) + (e & 7) * 2) = wv;
+                        const uint32_t row = a_stage + rr * A_SLAB;
+                        sts128(row, 0u, 0u, 0u, 0u);
+                        sts128(row + 16, 0u, 0u, 0u, 0u);
+                        const int r = (R0 + rr) - Y0;              // window row held by this source row
+                        if (cols_hit && r >= 0 && r <= K) {
+                            uint32_t wv[K1 / 2];
+#pragma unroll
+                            for (int wq = 0; wq < K1 / 2; ++wq) wv[wq] = lds32(wsm_a + (r * (K1 / 2) + wq) * 512);
+#pragma unroll
+                            for (int c = 0; c < K1; ++c) {
+                                const int e = e0 + c;
+                                if (e >= 0 && e < BW) {
+                                    const uint32_t half = (c & 1) ? (wv[c >> 1] >> 16) : (wv[c >> 1] & 0xffffu);
+                                    sts16(row + ((((e >> 3) << 4) ^ swz)) + (e & 7) * 2, half);
                                 }
                             }
                         }
@@ -347,6 +393,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                     fence_proxy_async_smem();
                     mbar_arrive(&full_a[slot]);
                 }
+            }
         }
     } else {
         // ================================================================= epilogue
@@ -375,7 +422,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                 uint32_t v[32];
                 tmem_ld_32x32(taddr + cc * 32, v);
                 tmem_ld_wait();
-                if (valid && regular) {
+                if (valid && regular && !(prefetch_mode & 256)) {   // bit 8: debug knob, skip the stores
                     if (NHWC) {
                         uint4* o4 = reinterpret_cast<uint4*>(o + cc * 32);
 #pragma unroll
@@ -398,29 +445,43 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            if (valid && !regular) {
-                // literal 4-tap path (same arithmetic as the gather kernel's fall-back)
+            // Pixels whose taps are not consecutive integers (fp32 rounding of (flow+offset)+coord straddling an
+            // integer: ~1e-5 of all pixels) keep the reference's literal 4-taps-per-(i,j) arithmetic.  One such pixel
+            // costs 100*CN dependent loads, so the whole warp shares it: lanes split the channels.
+            unsigned todo = __ballot_sync(0xffffffffu, valid && !regular);
+            while (todo) {
+                const int src_lane = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int qx = __shfl_sync(0xffffffffu, px, src_lane), qy = __shfl_sync(0xffffffffu, py, src_lane);
+                const float qfx = __shfl_sync(0xffffffffu, fx, src_lane), qfy = __shfl_sync(0xffffffffu, fy, src_lane);
+                const long long qofs = (long long)qy * W + qx;
                 float p[KK];
-                pixel_softmax_f32<KK>(logits + (long long)b * KK * hw + pofs, hw, p);
+                pixel_softmax_f32<KK>(logits + (long long)b * KK * hw + qofs, hw, p);   // every lane: same loads (broadcast)
+                AxisTap<float> tx[K], ty[K];
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    tx[j] = axis_tap<float>(qfx, j - K / 2, qx, Ws);
+                    ty[j] = axis_tap<float>(qfy, j - K / 2, qy, Hs);
+                }
                 const long long spl = (long long)Hs * Ws;
-                // element strides of source for (channel, position)
-                const long long sc = NHWC ? 1 : spl, sp = NHWC ? C : 1;
-                const __nv_bfloat16* s = NHWC ? src + (long long)b * spl * C + c0 : src + ((long long)b * C + c0) * spl;
-                for (int c = 0; c < CN; ++c, s += sc) {
+                const long long sc = NHWC ? 1 : spl, sp = NHWC ? C : 1;     // element strides: channel, position
+                const __nv_bfloat16* sb = NHWC ? src + (long long)b * spl * C + c0 : src + ((long long)b * C + c0) * spl;
+                __nv_bfloat16* ob = NHWC ? out + ((long long)b * hw + qofs) * C + c0 : out + ((long long)b * C + c0) * hw + qofs;
+                for (int c = lane; c < CN; c += 32) {
+                    const __nv_bfloat16* s = sb + c * sc;
                     float acc = 0.f;
-                    for (int i = 0; i < K; ++i) {
-                        const AxisTap<float> ty = axis_tap<float>(fy, i - K / 2, py, Hs);
+#pragma unroll
+                    for (int i = 0; i < K; ++i)
+#pragma unroll
                         for (int j = 0; j < K; ++j) {
-                            const AxisTap<float> tx = axis_tap<float>(fx, j - K / 2, px, Ws);
                             float v = 0.f;
-                            v += tx.wlo * ty.wlo * __bfloat162float(s[(ty.lo * Ws + tx.lo) * sp]);
-                            v += tx.whi * ty.wlo * __bfloat162float(s[(ty.lo * Ws + tx.hi) * sp]);
-                            v += tx.wlo * ty.whi * __bfloat162float(s[(ty.hi * Ws + tx.lo) * sp]);
-                            v += tx.whi * ty.whi * __bfloat162float(s[(ty.hi * Ws + tx.hi) * sp]);
+                            v += tx[j].wlo * ty[i].wlo * __bfloat162float(s[(ty[i].lo * Ws + tx[j].lo) * sp]);
+                            v += tx[j].whi * ty[i].wlo * __bfloat162float(s[(ty[i].lo * Ws + tx[j].hi) * sp]);
+                            v += tx[j].wlo * ty[i].whi * __bfloat162float(s[(ty[i].hi * Ws + tx[j].lo) * sp]);
+                            v += tx[j].whi * ty[i].whi * __bfloat162float(s[(ty[i].hi * Ws + tx[j].hi) * sp]);
                             acc += p[i * K + j] * v;
                         }
-                    }
-                    o[NHWC ? (long long)c : (long long)c * hw] = __float2bfloat16_rn(acc * (1.0f / static_cast<float>(KK)));
+                    ob[NHWC ? (long long)c : (long long)c * hw] = __float2bfloat16_rn(acc * (1.0f / static_cast<float>(KK)));
                 }
             }
         }
@@ -428,6 +489,12 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 2 * CN >= 32 ? 2 * CN : 32);
+}
+
+// tuning knobs (read once per process): GFLA_TC_PREFETCH = 0 none, 1 TMA tensor prefetch, 2 bulk row prefetch
+static int tune_knob(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
 }
 
 template <int K, int CN, bool NHWC>
@@ -461,7 +528,7 @@ static int launch_tc(const void* src, const void* flow, const void* logits, void
     dim3 grid((unsigned)min(ngroups, sm_count()), (unsigned)(C / CN));
     kern<<<grid, NTHREADS, Smem<CN>::ALLOC, st_>>>(tmap, (const __nv_bfloat16*)src, (const float*)flow,
                                                    (const __nv_bfloat16*)logits, (__nv_bfloat16*)out,
-                                                   (__nv_bfloat16*)probs, B, C, Hs, Ws, H, W);
+                                                   (__nv_bfloat16*)probs, B, C, Hs, Ws, H, W, tune_knob("GFLA_TC_PREFETCH", 2));
     return launch_status();
 }
 

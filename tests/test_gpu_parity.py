@@ -458,3 +458,48 @@ def test_local_attn_channels_last_gather_and_backward(F_, oracle_lib, dt):
     np.testing.assert_allclose(host(gs), ogs, rtol=10 * tol_, atol=10 * tol_)
     np.testing.assert_allclose(host(gl), ogl, rtol=10 * tol_, atol=10 * tol_)
     np.testing.assert_allclose(host(gf), ogf, rtol=20 * tol_, atol=20 * tol_ * max(1.0, np.abs(ogf).max()))
+
+
+def _irregular_flow_values(xs, k, rng):
+    """flows f (for pixel column x) for which the reference's fp32 tap arithmetic
+    floor((f + (j - k//2)) + x) is NOT consecutive in j: the rounding of the two additions straddles an
+    integer for some taps only (block_extractor_kernel.cu:62-69).  The kernels must follow it bit for bit."""
+    out = {}
+    for x in xs:
+        for n in (-3, 0, 2, 5):
+            for _ in range(4000):
+                f = np.float32(np.float32(n) + np.float32(rng.uniform(-4e-6, 4e-6)))
+                fl = [int(np.floor(np.float32(np.float32(f + np.float32(j - k // 2)) + np.float32(x)))) for j in range(k)]
+                if any(fl[j] != fl[0] + j for j in range(k)):
+                    out[x] = float(f)
+                    break
+            if x in out:
+                break
+    return out
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_local_attn_tile_irregular_taps(F_, oracle_lib, layout):
+    """pixels whose taps are not consecutive integers take the literal 4-tap path inside the tile kernel
+    (warp-cooperative): results still match the oracle, i.e. the reference's tap selection is kept."""
+    rng = np.random.default_rng(42)
+    B, C, H, W, k = 1, 64, 24, 64, 5
+    vals = _irregular_flow_values(range(3, W - 3, 2), k, rng)
+    assert len(vals) >= 10
+    flow = rng.uniform(-3, 3, (B, 2, H, W)).astype(np.float32)
+    n_irr = 0
+    for i, (x, f) in enumerate(vals.items()):
+        y = (5 * i) % H
+        flow[0, 0, y, x] = f                       # irregular along x
+        flow[0, 1, (y + 3) % H, x] = np.float32(_irregular_flow_values([(y + 3) % H], k, rng).get((y + 3) % H, 0.25))
+        n_irr += 1
+    s = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32)).to(DEV).bfloat16()
+    if layout == "nhwc":
+        s = s.contiguous(memory_format=torch.channels_last)
+    f = torch.from_numpy(flow).to(DEV)
+    l = torch.from_numpy(rng.standard_normal((B, k * k, H, W)).astype(np.float32)).to(DEV).bfloat16()
+    out = F_.local_attn_fwd(s, f, l, k, algo="tile")
+    ref = oracle_lib.local_attn_fwd(host(s), flow, host(l), k)
+    np.testing.assert_allclose(host(out), ref, rtol=0, atol=1e-2)
+    g = F_.local_attn_fwd(s, f, l, k, algo="gather")
+    assert (out.float() - g.float()).abs().max().item() <= 3e-3
