@@ -10,9 +10,12 @@ int attn_reshape_bwd(const void*, void*, int, int, int, int, int, int, cudaStrea
 int resample2d_fwd(const void*, const void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int resample2d_bwd(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int local_attn_fwd_gather(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
-int local_attn_bwd_gather(const void*, const void*, const void*, const void*, void*, void*, void*, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int local_attn_bwd_gather(const void*, const void*, const void*, const void*, void*, void*, void*, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+bool local_attn_bwd_tc_supported(int C, int k, int dtype, int flow_dtype, int layout, const void* gout, const void* gsrc);
+int local_attn_bwd_gs_tc(const void* flow, const void* logits, const void* gout, void* gsrc, int B, int C, int Hs, int Ws, int H, int W, int k, cudaStream_t);
 int local_attn_fwd_tc(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int tc_debug_set_buffer(void*);
+int tc_debug_set_buffer_bwd(void*);
 bool local_attn_fwd_tc_supported(int B, int C, int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, int layout, const void* src, const void* out);
 }  // namespace gfla
 
@@ -49,7 +52,10 @@ int gfla_device_check(void) {
     return (major == 10 && minor == 0) ? GFLA_OK : static_cast<int>(cudaErrorNoKernelImageForDevice);
 }
 
-int gfla_debug_set_buffer(void* host_mapped_u64x8) { return tc_debug_set_buffer(host_mapped_u64x8); }
+int gfla_debug_set_buffer(void* host_mapped_u64x8) {
+    const int e = tc_debug_set_buffer(host_mapped_u64x8);
+    return e ? e : tc_debug_set_buffer_bwd(host_mapped_u64x8);
+}
 
 int gfla_block_extract_fwd(const void* source, const void* flow, void* out, int B, int C, int Hs, int Ws, int Hf,
                            int Wf, int k, int dtype, int flow_dtype, gfla_stream_t stream) {
@@ -134,11 +140,20 @@ int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits
     if (!pos(B) || !pos(C) || !pos(Hs) || !pos(Ws) || !pos(H) || !pos(W) || k < 1 || k > 9) return GFLA_E_SHAPE;
     if (!dtype_known(dtype) || !flow_dtype_ok(dtype, flow_dtype)) return GFLA_E_DTYPE;
     if (algo < 0 || algo > 2) return GFLA_E_NOTSUP;
-    if (algo == 2) return GFLA_E_NOTSUP;  // no tile kernel for the backward yet
     REQ_ALIGN(source, dtype); REQ_ALIGN(logits, dtype); REQ_ALIGN(grad_out, dtype); REQ_ALIGN(grad_source, dtype);
     REQ_ALIGN(grad_logits, dtype); REQ_ALIGN(flow, flow_dtype); REQ_ALIGN(grad_flow, flow_dtype);
+    const bool tc_ok = local_attn_bwd_tc_supported(C, k, dtype, flow_dtype, layout, grad_out, grad_source);
+    if (algo == 2 && !tc_ok) return GFLA_E_NOTSUP;
+    if (algo == 2 || (algo == 0 && tc_ok)) {
+        // grad_source: tile kernel (GEMM + TMA reduce-add); grad_flow / grad_logits: per-pixel dot products
+        if (!accumulate) cudaMemsetAsync(grad_source, 0, (size_t)B * C * Hs * Ws * elem_size(dtype), (cudaStream_t)stream);
+        int e = local_attn_bwd_gs_tc(flow, logits, grad_out, grad_source, B, C, Hs, Ws, H, W, k, (cudaStream_t)stream);
+        if (e != GFLA_OK) return e;
+        return local_attn_bwd_gather(source, flow, logits, grad_out, grad_source, grad_flow, grad_logits, B, C, Hs, Ws, H,
+                                     W, k, dtype, flow_dtype, accumulate, layout, /*do_gs=*/0, (cudaStream_t)stream);
+    }
     return local_attn_bwd_gather(source, flow, logits, grad_out, grad_source, grad_flow, grad_logits, B, C, Hs, Ws, H, W,
-                                 k, dtype, flow_dtype, accumulate, layout, (cudaStream_t)stream);
+                                 k, dtype, flow_dtype, accumulate, layout, /*do_gs=*/1, (cudaStream_t)stream);
 }
 
 }  // extern "C"

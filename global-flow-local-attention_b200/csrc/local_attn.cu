@@ -157,7 +157,7 @@ template <typename T, typename TF, int K>
 __global__ void __launch_bounds__(128)
 k_local_attn_bwd(const T* __restrict__ src, const TF* __restrict__ flow, const T* __restrict__ logits,
                  const T* __restrict__ gout, T* __restrict__ gsrc, TF* __restrict__ gflow, T* __restrict__ glogits,
-                 int B, int C, int Hs, int Ws, int H, int W, int k_rt, int accumulate, int nhwc) {
+                 int B, int C, int Hs, int Ws, int H, int W, int k_rt, int accumulate, int nhwc, int do_gs) {
     using A = typename Acc<T>::type;
     const int k = K ? K : k_rt, KK = k * k;
     const long long hw = (long long)H * W, total = (long long)B * hw;
@@ -220,7 +220,7 @@ k_local_attn_bwd(const T* __restrict__ src, const TF* __restrict__ flow, const T
                     for (int q = 0; q < K1; ++q) {
                         const int o = cy[r] + cx[q];
                         Q[r * K1 + q] += g * ld(s + o);
-                        red_add(gs + o, g * Wc[r * K1 + q]);
+                        if (do_gs) red_add(gs + o, g * Wc[r * K1 + q]);
                     }
             }
 #pragma unroll
@@ -252,10 +252,12 @@ k_local_attn_bwd(const T* __restrict__ src, const TF* __restrict__ flow, const T
                     const A g = ld(goc);
                     qLT += g * ld(sq + oLT); qRT += g * ld(sq + oRT); qLB += g * ld(sq + oLB); qRB += g * ld(sq + oRB);
                     const A gp = g * pij;
-                    red_add(gc + oLT, gp * (tx.wlo * ty.wlo));
-                    red_add(gc + oRT, gp * (tx.whi * ty.wlo));
-                    red_add(gc + oLB, gp * (tx.wlo * ty.whi));
-                    red_add(gc + oRB, gp * (tx.whi * ty.whi));
+                    if (do_gs) {
+                        red_add(gc + oLT, gp * (tx.wlo * ty.wlo));
+                        red_add(gc + oRT, gp * (tx.whi * ty.wlo));
+                        red_add(gc + oLB, gp * (tx.wlo * ty.whi));
+                        red_add(gc + oRB, gp * (tx.whi * ty.whi));
+                    }
                 }
                 dp[i * k + j] = inv_kk * (ty.wlo * (tx.wlo * qLT + tx.whi * qRT) + ty.whi * (tx.wlo * qLB + tx.whi * qRB));
                 gfy += pij * (-tx.wlo * qLT - tx.whi * qRT + tx.wlo * qLB + tx.whi * qRB);
@@ -292,12 +294,12 @@ static int la_launch_fwd(const void* src, const void* flow, const void* logits, 
 template <typename T, typename TF, int K>
 static int la_launch_bwd(const void* src, const void* flow, const void* logits, const void* gout, void* gsrc,
                          void* gflow, void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate,
-                         int nhwc, cudaStream_t st_) {
+                         int nhwc, int do_gs, cudaStream_t st_) {
     const long long total = (long long)B * H * W;
     const int threads = 128;
     k_local_attn_bwd<T, TF, K><<<(unsigned)((total + threads - 1) / threads), threads, 0, st_>>>(
         (const T*)src, (const TF*)flow, (const T*)logits, (const T*)gout, (T*)gsrc, (TF*)gflow, (T*)glogits, B, C, Hs,
-        Ws, H, W, k, accumulate, nhwc);
+        Ws, H, W, k, accumulate, nhwc, do_gs);
     return launch_status();
 }
 
@@ -317,9 +319,9 @@ static int la_fwd_k(const void* src, const void* flow, const void* logits, void*
 }
 template <typename T, typename TF>
 static int la_bwd_k(const void* src, const void* flow, const void* logits, const void* gout, void* gsrc, void* gflow,
-                    void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate, int nhwc,
+                    void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate, int nhwc, int do_gs,
                     cudaStream_t st_) {
-    GFLA_K_DISPATCH(la_launch_bwd, src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, k, accumulate, nhwc, st_)
+    GFLA_K_DISPATCH(la_launch_bwd, src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, k, accumulate, nhwc, do_gs, st_)
 }
 
 int local_attn_fwd_gather(const void* src, const void* flow, const void* logits, void* out, void* probs, int B, int C,
@@ -333,13 +335,14 @@ int local_attn_fwd_gather(const void* src, const void* flow, const void* logits,
 
 int local_attn_bwd_gather(const void* src, const void* flow, const void* logits, const void* gout, void* gsrc,
                           void* gflow, void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int dtype,
-                          int flow_dtype, int accumulate, int layout, cudaStream_t st_) {
+                          int flow_dtype, int accumulate, int layout, int do_gs, cudaStream_t st_) {
+    // do_gs = 0: grad_source is produced elsewhere (tile kernel); only grad_flow / grad_logits here
     const int nhwc = layout == GFLA_NHWC;
-    if (!accumulate) cudaMemsetAsync(gsrc, 0, (size_t)B * C * Hs * Ws * elem_size(dtype), st_);
+    if (!accumulate && do_gs) cudaMemsetAsync(gsrc, 0, (size_t)B * C * Hs * Ws * elem_size(dtype), st_);
     return GFLA_DISPATCH_T(dtype, [&]() -> int {
         if (flow_dtype == dtype)
-            return la_bwd_k<T, T>(src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, k, accumulate, nhwc, st_);
-        return la_bwd_k<T, float>(src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, k, accumulate, nhwc, st_);
+            return la_bwd_k<T, T>(src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, k, accumulate, nhwc, do_gs, st_);
+        return la_bwd_k<T, float>(src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, k, accumulate, nhwc, do_gs, st_);
     });
 }
 

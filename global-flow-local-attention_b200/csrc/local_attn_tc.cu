@@ -35,45 +35,16 @@
 //               pixels whose taps are not consecutive integers (fp32 rounding
 //               straddling an integer -- measure-zero) are recomputed here with
 //               the literal 4-tap path so indexing stays bit-identical.
-#include <climits>
-#include <cstdlib>
-
-#include "common.cuh"
-#include "tc_common.cuh"
+#include "tile_window.cuh"
 
 namespace gfla {
 
 namespace tc {
 
-constexpr int GW = 16, GH = 8;          // pixel group (M = 128)
-constexpr int BW = 16;                  // positions per row segment = 32-byte swizzle span in bf16 = K of one MMA
 constexpr int RCH = 2;                  // source rows per pipeline stage
 constexpr int NSTAGE = 8;
 constexpr int NINFO = 16;               // >= NSTAGE + 3 (producer run-ahead + 2 accumulators in flight)
 constexpr int NTHREADS = 320;
-constexpr int A_SLAB = 128 * 32;        // bytes: [128 pixels][16 positions] bf16, 32B rows, 32B swizzle
-
-struct GroupInfo { int x0, y0, ncb, nrc; };
-
-// softmax over the KK logits of one pixel (bf16 planes, stride hw), fp32 arithmetic
-template <int KK>
-__device__ __forceinline__ void pixel_softmax_f32(const __nv_bfloat16* __restrict__ lg, long long hw, float* p) {
-    float mx = -INFINITY;
-#pragma unroll
-    for (int t = 0; t < KK; ++t) {
-        p[t] = __bfloat162float(lg[t * hw]);
-        mx = fmaxf(mx, p[t]);
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int t = 0; t < KK; ++t) {
-        p[t] = expf(p[t] - mx);
-        sum += p[t];
-    }
-    const float inv = 1.0f / sum;
-#pragma unroll
-    for (int t = 0; t < KK; ++t) p[t] *= inv;
-}
 
 template <int CN>
 struct Smem {
@@ -90,19 +61,6 @@ struct Smem {
     static constexpr int TOTAL = OFF_TMEM + 16;
     static constexpr int ALLOC = TOTAL + 1024;               // slack to align the base to 1024 B
 };
-
-template <int K>
-__device__ __forceinline__ bool taps_regular(float flow_x, float flow_y, int x, int y, int Hs, int Ws,
-                                             AxisTap<float> (&tx)[K], AxisTap<float> (&ty)[K]) {
-    bool regular = true;
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-        tx[j] = axis_tap<float>(flow_x, j - K / 2, x, Ws);
-        ty[j] = axis_tap<float>(flow_y, j - K / 2, y, Hs);
-        regular = regular && (tx[j].fl == tx[0].fl + j) && (ty[j].fl == ty[0].fl + j);
-    }
-    return regular;
-}
 
 // NHWC = channels-last storage of source / out (logical shapes stay [B,C,H,W]): every source position is
 // 2*C contiguous bytes, so the TMA boxes [64 channels][16 x] are made of 128-byte runs (the NCHW variant has
@@ -151,37 +109,13 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
 
     if (warp == 0) {
         // ================================================================= producer
-        // bounding box (clamped tap positions) of one pixel group: warp-collective
-        auto group_bbox = [&](int g, int& x0, int& y0, int& x1, int& y1) {
-            const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
-            int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int m = lane + 32 * i, px = gx0 + (m & 15), py = gy0 + (m >> 4);
-                if (px < W && py < H) {
-                    const long long o = (long long)b * 2 * hw + (long long)py * W + px;
-                    const float fx = flow[o], fy = flow[o + hw];
-                    xmin = min(xmin, axis_tap<float>(fx, -(K / 2), px, Ws).lo);
-                    xmax = max(xmax, axis_tap<float>(fx, K - 1 - K / 2, px, Ws).hi);
-                    ymin = min(ymin, axis_tap<float>(fy, -(K / 2), py, Hs).lo);
-                    ymax = max(ymax, axis_tap<float>(fy, K - 1 - K / 2, py, Hs).hi);
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
-                xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
-                ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
-                ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
-            }
-            // TMA needs the innermost start coordinate on a 16-byte boundary: in NCHW that is x (8 bf16)
-            if (!NHWC) xmin &= ~7;
-            x0 = xmin; y0 = ymin; x1 = xmax; y1 = ymax;
+        auto bbox_of = [&](int g, int& x0, int& y0, int& x1, int& y1) {
+            group_bbox<K>(flow, g / (gxn * gyn), (g % gxn) * GW, ((g / gxn) % gyn) * GH, H, W, Hs, Ws, lane, !NHWC, x0, y0, x1, y1);
         };
         uint32_t it = 0;  // global stage counter
         int gi = 0;
         int nx0 = 0, ny0 = 0, nx1 = 0, ny1 = 0;
-        if ((int)blockIdx.x < ngroups) group_bbox(blockIdx.x, nx0, ny0, nx1, ny1);
+        if ((int)blockIdx.x < ngroups) bbox_of(blockIdx.x, nx0, ny0, nx1, ny1);
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
             const int b = g / (gxn * gyn);
             const int xmin = nx0, ymin = ny0, xmax = nx1, ymax = ny1;
@@ -189,7 +123,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             // rows yet, so pull them into L2 now -- a whole group of time before the TMA loads need them
             const int gn = g + gridDim.x;
             if (gn < ngroups) {
-                group_bbox(gn, nx0, ny0, nx1, ny1);
+                bbox_of(gn, nx0, ny0, nx1, ny1);
                 const int bn = gn / (gxn * gyn), prow = ny1 - ny0 + 1;
                 if ((prefetch_mode & 255) == 2 && NHWC && CN == C) {
                     // channels-last, all channels in this CTA: a row segment of the box is one contiguous range
@@ -299,65 +233,10 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                 const float fx = flow[(long long)b * 2 * hw + pofs], fy = flow[(long long)b * 2 * hw + hw + pofs];
                 AxisTap<float> tx[K], ty[K];
                 live = taps_regular<K>(fx, fy, px, py, Hs, Ws, tx, ty);
-                X0 = tx[0].fl;
-                Y0 = ty[0].fl;
                 if (live) {
-                    // collapsed window, separably: rows of x-weights first, then the y-weights
                     float w[K1 * K1];
-#pragma unroll
-                    for (int i = 0; i < K1 * K1; ++i) w[i] = 0.f;
-#pragma unroll
-                    for (int i = 0; i < K; ++i) {
-                        float rowx[K1];
-#pragma unroll
-                        for (int s2 = 0; s2 < K1; ++s2) rowx[s2] = 0.f;
-#pragma unroll
-                        for (int j = 0; j < K; ++j) {
-                            const float pij = p[i * K + j] * inv_kk;
-                            rowx[j] += pij * tx[j].wlo;
-                            rowx[j + 1] += pij * tx[j].whi;
-                        }
-#pragma unroll
-                        for (int s2 = 0; s2 < K1; ++s2) {
-                            w[i * K1 + s2] += ty[i].wlo * rowx[s2];
-                            w[(i + 1) * K1 + s2] += ty[i].whi * rowx[s2];
-                        }
-                    }
-                    // replicate border (only pixels whose window crosses the image edge): fold the weights of
-                    // out-of-range columns / rows onto the border position
-                    if (X0 < 0 || X0 + K > Ws - 1 || Y0 < 0 || Y0 + K > Hs - 1) {
-#pragma unroll
-                        for (int r = 0; r < K1; ++r) {
-#pragma unroll
-                            for (int s2 = 0; s2 < K; ++s2)
-                                if (X0 + s2 < 0) { w[r * K1 + s2 + 1] += w[r * K1 + s2]; w[r * K1 + s2] = 0.f; }
-#pragma unroll
-                            for (int s2 = K; s2 > 0; --s2)
-                                if (X0 + s2 > Ws - 1) { w[r * K1 + s2 - 1] += w[r * K1 + s2]; w[r * K1 + s2] = 0.f; }
-                        }
-#pragma unroll
-                        for (int s2 = 0; s2 < K1; ++s2) {
-#pragma unroll
-                            for (int r = 0; r < K; ++r)
-                                if (Y0 + r < 0) { w[(r + 1) * K1 + s2] += w[r * K1 + s2]; w[r * K1 + s2] = 0.f; }
-#pragma unroll
-                            for (int r = K; r > 0; --r)
-                                if (Y0 + r > Hs - 1) { w[(r - 1) * K1 + s2] += w[r * K1 + s2]; w[r * K1 + s2] = 0.f; }
-                        }
-                    }
-                    // a window lying entirely outside the image has been folded onto its last (first) column /
-                    // row, which belongs on border position 0 (Ws-1, Hs-1): shift the origin accordingly so that
-                    // "window column s <-> source position X0 + s" holds for every non-zero weight
-                    X0 = min(max(X0, -K), Ws - 1);
-                    Y0 = min(max(Y0, -K), Hs - 1);
-                    // pack each window row as bf16x2 words (K1 = 6 -> 3 words, K1 = 4 -> 2 words)
-#pragma unroll
-                    for (int r = 0; r < K1; ++r)
-#pragma unroll
-                        for (int wq = 0; wq < K1 / 2; ++wq) {
-                            const __nv_bfloat162 v2 = __floats2bfloat162_rn(w[r * K1 + 2 * wq], w[r * K1 + 2 * wq + 1]);
-                            sts32(wsm_a + (r * (K1 / 2) + wq) * 512, *reinterpret_cast<const uint32_t*>(&v2));
-                        }
+                    build_window<K>(p, tx, ty, Hs, Ws, inv_kk, w, X0, Y0);
+                    store_window_words<K>(wsm_a, w);
                 }
             }
             mbar_wait(&info_full[gi % NINFO], (gi / NINFO) & 1, 0x020500, gi);
@@ -371,25 +250,8 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                     const uint32_t a_stage = a_base + slot * SM::A_STAGE;
                     const int R0 = inf.y0 + rc * RCH;
 #pragma unroll
-                    for (int rr = 0; rr < RCH; ++rr) {
-                        const uint32_t row = a_stage + rr * A_SLAB;
-                        sts128(row, 0u, 0u, 0u, 0u);
-                        sts128(row + 16, 0u, 0u, 0u, 0u);
-                        const int r = (R0 + rr) - Y0;              // window row held by this source row
-                        if (cols_hit && r >= 0 && r <= K) {
-                            uint32_t wv[K1 / 2];
-#pragma unroll
-                            for (int wq = 0; wq < K1 / 2; ++wq) wv[wq] = lds32(wsm_a + (r * (K1 / 2) + wq) * 512);
-#pragma unroll
-                            for (int c = 0; c < K1; ++c) {
-                                const int e = e0 + c;
-                                if (e >= 0 && e < BW) {
-                                    const uint32_t half = (c & 1) ? (wv[c >> 1] >> 16) : (wv[c >> 1] & 0xffffu);
-                                    sts16(row + ((((e >> 3) << 4) ^ swz)) + (e & 7) * 2, half);
-                                }
-                            }
-                        }
-                    }
+                    for (int rr = 0; rr < RCH; ++rr)
+                        fill_slab_row<K>(a_stage + rr * A_SLAB, swz, wsm_a, cols_hit, (R0 + rr) - Y0, e0);
                     fence_proxy_async_smem();
                     mbar_arrive(&full_a[slot]);
                 }
@@ -491,12 +353,6 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
     if (warp == 1) tmem_dealloc(tmem_base, 2 * CN >= 32 ? 2 * CN : 32);
 }
 
-// tuning knobs (read once per process): GFLA_TC_PREFETCH = 0 none, 1 TMA tensor prefetch, 2 bulk row prefetch
-static int tune_knob(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
-
 template <int K, int CN, bool NHWC>
 static int launch_tc(const void* src, const void* flow, const void* logits, void* out, void* probs, int B, int C, int Hs,
                      int Ws, int H, int W, cudaStream_t st_) {
@@ -528,7 +384,7 @@ static int launch_tc(const void* src, const void* flow, const void* logits, void
     dim3 grid((unsigned)min(ngroups, sm_count()), (unsigned)(C / CN));
     kern<<<grid, NTHREADS, Smem<CN>::ALLOC, st_>>>(tmap, (const __nv_bfloat16*)src, (const float*)flow,
                                                    (const __nv_bfloat16*)logits, (__nv_bfloat16*)out,
-                                                   (__nv_bfloat16*)probs, B, C, Hs, Ws, H, W, tune_knob("GFLA_TC_PREFETCH", 2));
+                                                   (__nv_bfloat16*)probs, B, C, Hs, Ws, H, W, tune_knob("GFLA_TC_PREFETCH", 0));
     return launch_status();
 }
 

@@ -38,7 +38,7 @@ static __device__ unsigned long long* g_tc_dbg = nullptr;
 
 // Bounded wait: a protocol bug must abort the kernel (trap -> launch error), never hang the GPU.
 // `tag` identifies the waiter (role << 16 | barrier kind << 8 | slot) in the debug buffer.
-__device__ __noinline__ void mbar_timeout(uint32_t tag, uint32_t parity, uint32_t iter) {
+static __device__ __noinline__ void mbar_timeout(uint32_t tag, uint32_t parity, uint32_t iter) {
     unsigned long long* d = g_tc_dbg;
     if (d != nullptr) {
         if (atomicCAS(d, 0ull, (unsigned long long)tag | (1ull << 63)) == 0ull) {

@@ -1,0 +1,181 @@
+// Pieces shared by the forward and backward tile kernels: pixel-group geometry, per-pixel softmax,
+// the reference's tap arithmetic, the collapsed (k+1)x(k+1) weight window and its scatter into the
+// [128 pixels][16 positions] UMMA weight slabs.
+#pragma once
+#include <climits>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace gfla {
+namespace tc {
+
+constexpr int GW = 16, GH = 8;          // pixel group: 16 x 8 = 128 pixels (= M or K of the MMAs)
+constexpr int BW = 16;                  // source positions per row segment = 32-byte swizzle span in bf16 = one MMA K
+constexpr int A_SLAB = 128 * 32;        // bytes: [128 pixels][16 positions] bf16, 32B rows, 32B swizzle
+
+struct GroupInfo { int x0, y0, ncb, nrc; };
+
+// softmax over the KK logits of one pixel (bf16 planes, stride hw), fp32 arithmetic
+template <int KK>
+__device__ __forceinline__ void pixel_softmax_f32(const __nv_bfloat16* __restrict__ lg, long long hw, float* p) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < KK; ++t) {
+        p[t] = __bfloat162float(lg[t * hw]);
+        mx = fmaxf(mx, p[t]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < KK; ++t) {
+        p[t] = expf(p[t] - mx);
+        sum += p[t];
+    }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int t = 0; t < KK; ++t) p[t] *= inv;
+}
+
+// the k taps per axis, evaluated exactly like the reference; "regular" = consecutive integers
+template <int K>
+__device__ __forceinline__ bool taps_regular(float flow_x, float flow_y, int x, int y, int Hs, int Ws,
+                                             AxisTap<float> (&tx)[K], AxisTap<float> (&ty)[K]) {
+    bool regular = true;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        tx[j] = axis_tap<float>(flow_x, j - K / 2, x, Ws);
+        ty[j] = axis_tap<float>(flow_y, j - K / 2, y, Hs);
+        regular = regular && (tx[j].fl == tx[0].fl + j) && (ty[j].fl == ty[0].fl + j);
+    }
+    return regular;
+}
+
+// bounding box (clamped tap positions) of one 16x8 pixel group: warp-collective.
+// align_x8: NCHW tensor maps need the innermost (x) box origin on a 16-byte boundary.
+template <int K>
+__device__ __forceinline__ void group_bbox(const float* __restrict__ flow, int b, int gx0, int gy0, int H, int W, int Hs,
+                                           int Ws, int lane, bool align_x8, int& x0, int& y0, int& x1, int& y1) {
+    const long long hw = (long long)H * W;
+    int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = lane + 32 * i, px = gx0 + (m & 15), py = gy0 + (m >> 4);
+        if (px < W && py < H) {
+            const long long o = (long long)b * 2 * hw + (long long)py * W + px;
+            const float fx = flow[o], fy = flow[o + hw];
+            xmin = min(xmin, axis_tap<float>(fx, -(K / 2), px, Ws).lo);
+            xmax = max(xmax, axis_tap<float>(fx, K - 1 - K / 2, px, Ws).hi);
+            ymin = min(ymin, axis_tap<float>(fy, -(K / 2), py, Hs).lo);
+            ymax = max(ymax, axis_tap<float>(fy, K - 1 - K / 2, py, Hs).hi);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    if (align_x8) xmin &= ~7;
+    x0 = xmin; y0 = ymin; x1 = xmax; y1 = ymax;
+}
+
+// Collapsed window of one (regular) pixel: w[r][s] multiplies source position (Y0 + r, X0 + s).
+// p = softmax probabilities (already scaled by whatever the caller wants, e.g. 1/k^2).  Border handling =
+// the reference's index clamp: weights of out-of-range columns / rows are folded onto the border position.
+// On return X0 / Y0 are shifted so that the mapping also holds for windows lying entirely outside the image.
+template <int K>
+__device__ __forceinline__ void build_window(const float* p, const AxisTap<float> (&tx)[K], const AxisTap<float> (&ty)[K],
+                                             int Hs, int Ws, float scale, float* w, int& X0, int& Y0) {
+    constexpr int K1 = K + 1;
+#pragma unroll
+    for (int i = 0; i < K1 * K1; ++i) w[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {  // separably: x-weights of row i first, then spread over the two y-taps
+        float rowx[K1];
+#pragma unroll
+        for (int s = 0; s < K1; ++s) rowx[s] = 0.f;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const float pij = p[i * K + j] * scale;
+            rowx[j] += pij * tx[j].wlo;
+            rowx[j + 1] += pij * tx[j].whi;
+        }
+#pragma unroll
+        for (int s = 0; s < K1; ++s) {
+            w[i * K1 + s] += ty[i].wlo * rowx[s];
+            w[(i + 1) * K1 + s] += ty[i].whi * rowx[s];
+        }
+    }
+    X0 = tx[0].fl;
+    Y0 = ty[0].fl;
+    if (X0 < 0 || X0 + K > Ws - 1 || Y0 < 0 || Y0 + K > Hs - 1) {  // only pixels whose window crosses the image edge
+#pragma unroll
+        for (int r = 0; r < K1; ++r) {
+#pragma unroll
+            for (int s = 0; s < K; ++s)
+                if (X0 + s < 0) { w[r * K1 + s + 1] += w[r * K1 + s]; w[r * K1 + s] = 0.f; }
+#pragma unroll
+            for (int s = K; s > 0; --s)
+                if (X0 + s > Ws - 1) { w[r * K1 + s - 1] += w[r * K1 + s]; w[r * K1 + s] = 0.f; }
+        }
+#pragma unroll
+        for (int s = 0; s < K1; ++s) {
+#pragma unroll
+            for (int r = 0; r < K; ++r)
+                if (Y0 + r < 0) { w[(r + 1) * K1 + s] += w[r * K1 + s]; w[r * K1 + s] = 0.f; }
+#pragma unroll
+            for (int r = K; r > 0; --r)
+                if (Y0 + r > Hs - 1) { w[(r - 1) * K1 + s] += w[r * K1 + s]; w[r * K1 + s] = 0.f; }
+        }
+        // a window entirely outside the image has been folded onto its last (first) column / row, which
+        // belongs on border position 0 (Ws-1, Hs-1)
+        X0 = min(max(X0, -K), Ws - 1);
+        Y0 = min(max(Y0, -K), Hs - 1);
+    }
+}
+
+// window rows as packed bf16x2 words in shared memory: word (r*(K1/2) + q) of pixel m at wsm_a + idx*512
+template <int K>
+__device__ __forceinline__ void store_window_words(uint32_t wsm_a, const float* w) {
+    constexpr int K1 = K + 1;
+#pragma unroll
+    for (int r = 0; r < K1; ++r)
+#pragma unroll
+        for (int q = 0; q < K1 / 2; ++q) {
+            const __nv_bfloat162 v2 = __floats2bfloat162_rn(w[r * K1 + 2 * q], w[r * K1 + 2 * q + 1]);
+            sts32(wsm_a + (r * (K1 / 2) + q) * 512, *reinterpret_cast<const uint32_t*>(&v2));
+        }
+}
+
+// One 32-byte slab row (this pixel x 16 positions of one source row segment): zero it, then drop in the
+// window row r (if the segment holds any of its K+1 columns).  e0 = box position of window column 0.
+template <int K>
+__device__ __forceinline__ void fill_slab_row(uint32_t row, uint32_t swz, uint32_t wsm_a, bool hit, int r, int e0) {
+    constexpr int K1 = K + 1;
+    sts128(row, 0u, 0u, 0u, 0u);
+    sts128(row + 16, 0u, 0u, 0u, 0u);
+    if (hit && r >= 0 && r <= K) {
+        uint32_t wv[K1 / 2];
+#pragma unroll
+        for (int q = 0; q < K1 / 2; ++q) wv[q] = lds32(wsm_a + (r * (K1 / 2) + q) * 512);
+#pragma unroll
+        for (int c = 0; c < K1; ++c) {
+            const int e = e0 + c;
+            if (e >= 0 && e < BW) {
+                const uint32_t half = (c & 1) ? (wv[c >> 1] >> 16) : (wv[c >> 1] & 0xffffu);
+                sts16(row + ((((e >> 3) << 4) ^ swz)) + (e & 7) * 2, half);
+            }
+        }
+    }
+}
+
+// tuning knobs (environment, read per launch)
+inline int tune_knob(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+}  // namespace tc
+}  // namespace gfla

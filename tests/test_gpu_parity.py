@@ -503,3 +503,43 @@ def test_local_attn_tile_irregular_taps(F_, oracle_lib, layout):
     np.testing.assert_allclose(host(out), ref, rtol=0, atol=1e-2)
     g = F_.local_attn_fwd(s, f, l, k, algo="gather")
     assert (out.float() - g.float()).abs().max().item() <= 3e-3
+
+
+# ----------------------------------------------------------------------------- tile backward (grad_source GEMM + TMA reduce-add)
+@pytest.mark.parametrize("kind", ["smooth", "iid", "border", "zero"])
+@pytest.mark.parametrize("shape", [
+    (1, 64, 32, 32, 32, 32, 5),
+    (2, 256, 24, 40, 24, 40, 5),
+    (1, 128, 21, 27, 21, 27, 3),      # ragged groups, odd width
+    (1, 64, 24, 32, 19, 27, 3),       # source larger than the flow field
+    (1, 512, 16, 24, 16, 24, 5),      # two channel chunks
+])
+def test_local_attn_bwd_tile_vs_oracle(F_, oracle_lib, shape, kind):
+    B, C, Hs, Ws, H, W, k = shape
+    s, f, l = _tile_inputs(B, C, Hs, Ws, H, W, k, kind, seed=3 * sum(shape) + len(kind))
+    s = s.contiguous(memory_format=torch.channels_last)
+    rng = np.random.default_rng(7)
+    g = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32)).to(DEV).bfloat16()
+    g = g.contiguous(memory_format=torch.channels_last)
+    gs, gf, gl = F_.local_attn_bwd(s, f, l, g, k, algo="tile")
+    assert gs.is_contiguous(memory_format=torch.channels_last)
+    ogs, ogf, ogl = oracle_lib.local_attn_bwd(host(s), f.cpu().numpy(), host(l), host(g), k)
+    scale = max(1.0, float(np.abs(ogs).max()))
+    np.testing.assert_allclose(host(gs), ogs, rtol=0, atol=1e-2 * scale)      # bf16 storage + bf16 reduce-adds
+    np.testing.assert_allclose(host(gl), ogl, rtol=0, atol=1e-2)
+    np.testing.assert_allclose(host(gf), ogf, rtol=2e-2, atol=2e-2 * max(1.0, float(np.abs(ogf).max())))
+
+
+def test_local_attn_bwd_tile_irregular_taps(F_, oracle_lib):
+    rng = np.random.default_rng(43)
+    B, C, H, W, k = 1, 64, 24, 64, 5
+    vals = _irregular_flow_values(range(3, W - 3, 2), k, rng)
+    flow = rng.uniform(-3, 3, (B, 2, H, W)).astype(np.float32)
+    for i, (x, fv) in enumerate(vals.items()):
+        flow[0, 0, (5 * i) % H, x] = fv
+    s = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32)).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    g = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32)).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    l = torch.from_numpy(rng.standard_normal((B, k * k, H, W)).astype(np.float32)).to(DEV).bfloat16()
+    gs, gf, gl = F_.local_attn_bwd(s, torch.from_numpy(flow).to(DEV), l, g, k, algo="tile")
+    ogs, ogf, ogl = oracle_lib.local_attn_bwd(host(s), flow, host(l), host(g), k)
+    np.testing.assert_allclose(host(gs), ogs, rtol=0, atol=1e-2 * max(1.0, float(np.abs(ogs).max())))
