@@ -12,6 +12,8 @@ int resample2d_bwd(const void*, const void*, const void*, void*, void*, int, int
 int local_attn_fwd_gather(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int local_attn_bwd_gather(const void*, const void*, const void*, const void*, void*, void*, void*, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 bool local_attn_bwd_tc_supported(int C, int k, int dtype, int flow_dtype, int layout, const void* gout, const void* gsrc);
+bool local_attn_bwd_q_tc_supported(int C, int k);
+int local_attn_bwd_q_tc(const void* src, const void* flow, const void* logits, const void* gout, void* gflow, void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate, cudaStream_t);
 int local_attn_bwd_gs_tc(const void* flow, const void* logits, const void* gout, void* gsrc, int B, int C, int Hs, int Ws, int H, int W, int k, cudaStream_t);
 int local_attn_fwd_tc(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int tc_debug_set_buffer(void*);
@@ -149,6 +151,9 @@ int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits
         if (!accumulate) cudaMemsetAsync(grad_source, 0, (size_t)B * C * Hs * Ws * elem_size(dtype), (cudaStream_t)stream);
         int e = local_attn_bwd_gs_tc(flow, logits, grad_out, grad_source, B, C, Hs, Ws, H, W, k, (cudaStream_t)stream);
         if (e != GFLA_OK) return e;
+        if (local_attn_bwd_q_tc_supported(C, k))
+            return local_attn_bwd_q_tc(source, flow, logits, grad_out, grad_flow, grad_logits, B, C, Hs, Ws, H, W, k,
+                                       accumulate, (cudaStream_t)stream);
         return local_attn_bwd_gather(source, flow, logits, grad_out, grad_source, grad_flow, grad_logits, B, C, Hs, Ws, H,
                                      W, k, dtype, flow_dtype, accumulate, layout, /*do_gs=*/0, (cudaStream_t)stream);
     }
