@@ -313,7 +313,7 @@ def main():
                 "frac": ach / peak, "traffic": None, "algorithmic_bytes": nbytes, "launch_ms": ms}
 
     rf_fwd = roof(fwd_bytes, fwd_ms, "local_attn_fwd")
-    rf_bwd = roof(bwd_bytes, bwd_ms, "local_attn_bwd (+grad_source memset)")
+    rf_bwd = roof(bwd_bytes, bwd_ms, "local_attn_bwd: grad_source GEMM+TMA reduce-add, grad_flow/logits GEMM (+grad_source memset)")
     dominant = rf_bwd if bwd_ms >= fwd_ms else rf_fwd
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -321,7 +321,8 @@ def main():
             "roofline": dominant, "roofline_fwd": rf_fwd, "roofline_bwd": rf_bwd,
             "step_roofline_frac": (fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9 / peak,
             "clocks": sampler.summary(t_wall0, t_wall1),
-            "gpu_launches": 2 * steps, "e2e": e2e}
+            "gpu_launches": 4 * steps,   # fwd tile + grad_source tile + grad_flow/logits tile + memset node
+            "e2e": e2e}
     if world == 1 and not args.no_cpu_baseline:
         try:
             cb, _ = cpu_reference_run(steps=2, warmup=0, budget_s=20.0)

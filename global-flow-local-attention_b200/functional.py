@@ -170,12 +170,26 @@ def local_attn_fwd(source, flow, logits, k, return_probs=False, algo="auto"):
     return (out, probs) if return_probs else out
 
 
+def _tile_bwd_eligible(source, flow, k) -> bool:
+    """what the backward tile kernels serve (mirrors local_attn_bwd_tc_supported in csrc/local_attn_bwd_tc.cu)"""
+    c = source.shape[1]
+    return (source.dtype == torch.bfloat16 and flow.dtype == torch.float32 and k in (3, 5)
+            and (c % 256 == 0 or c in (64, 128)))
+
+
 def local_attn_bwd(source, flow, logits, grad_out, k, algo="auto"):
     layout = _feature_layout(source)
     assert flow.is_contiguous() and logits.is_contiguous()
+    _need_cuda(source, flow, logits, grad_out)
+    if layout == _lib.GFLA_NCHW and algo == "auto" and _tile_bwd_eligible(source, flow, k):
+        # The backward tile kernels are channels-last only (every operand must be channel-contiguous for TMA).
+        # For planar callers, re-lay the two feature tensors (two extra passes over them) instead of falling
+        # back to the scalar-atomics kernel: ~100x faster at cfg2.
+        gs, gf, gl = local_attn_bwd(source.contiguous(memory_format=torch.channels_last), flow, logits,
+                                    grad_out.contiguous(memory_format=torch.channels_last), k, algo="auto")
+        return gs.contiguous(), gf, gl
     fmt = torch.channels_last if layout == _lib.GFLA_NHWC else torch.contiguous_format
     grad_out = grad_out.contiguous(memory_format=fmt)
-    _need_cuda(source, flow, logits, grad_out)
     bs, ds, hs, ws = source.size()
     _, _, h, w = flow.size()
     gs, gf, gl = _like_layout(source, source.shape, layout), torch.empty_like(flow), torch.empty_like(logits)

@@ -543,3 +543,17 @@ def test_local_attn_bwd_tile_irregular_taps(F_, oracle_lib):
     gs, gf, gl = F_.local_attn_bwd(s, torch.from_numpy(flow).to(DEV), l, g, k, algo="tile")
     ogs, ogf, ogl = oracle_lib.local_attn_bwd(host(s), flow, host(l), host(g), k)
     np.testing.assert_allclose(host(gs), ogs, rtol=0, atol=1e-2 * max(1.0, float(np.abs(ogs).max())))
+
+
+def test_local_attn_bwd_nchw_bf16_routes_through_tile_kernels(F_, oracle_lib):
+    """planar (NCHW) bf16 callers: 'auto' re-lays the feature tensors and uses the tile kernels; results come
+    back contiguous NCHW and match the oracle like the channels_last path"""
+    B, C, H, W, k = 1, 64, 24, 32, 5
+    s, f, l = _tile_inputs(B, C, H, W, H, W, k, "smooth", seed=99)
+    g = torch.randn(B, C, H, W, device=DEV).bfloat16()
+    gs, gf, gl = F_.local_attn_bwd(s, f, l, g, k)
+    assert gs.is_contiguous()
+    ogs, ogf, ogl = oracle_lib.local_attn_bwd(host(s), f.cpu().numpy(), host(l), host(g), k)
+    np.testing.assert_allclose(host(gs), ogs, rtol=0, atol=1e-2 * max(1.0, float(np.abs(ogs).max())))
+    np.testing.assert_allclose(host(gl), ogl, rtol=0, atol=1e-2)
+    np.testing.assert_allclose(host(gf), ogf, rtol=2e-2, atol=2e-2 * max(1.0, float(np.abs(ogf).max())))
