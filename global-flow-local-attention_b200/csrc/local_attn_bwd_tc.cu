@@ -61,6 +61,9 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* m, uint32_t
     asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void red_add_bf16x2(void* gptr, uint32_t v) {
+    asm volatile("red.global.add.noftz.bf16x2 [%0], %1;" ::"l"(gptr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -171,7 +174,7 @@ k_local_attn_bwd_gs_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         const uint32_t wsm_a = smem_u32(smem + SM::OFF_W) + m * 4;
         const uint32_t a_base = smem_u32(smem + SM::OFF_A) + m * 32;
         const uint32_t swz = ((m >> 2) & 1) << 4;
-        uint32_t blk = 0;
+        uint32_t blk = 0, dirty = 0xffffffffu;
         int gi = 0;
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
             const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
@@ -202,10 +205,12 @@ k_local_attn_bwd_gs_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                     mbar_wait(&a_empty[st], ((blk / GS_NA) & 1) ^ 1, 0x020200 | st, blk);
                     const uint32_t a_stage = a_base + st * SM::A_STAGE;
                     const int R0 = inf.y0 + rb * GS_ROWS;
+                    bool wrote = false;
 #pragma unroll
                     for (int seg = 0; seg < GS_ROWS; ++seg)
-                        fill_slab_row<K>(a_stage + seg * A_SLAB, swz, wsm_a, cols_hit, (R0 + seg) - Y0, e0);
-                    fence_proxy_async_smem();
+                        wrote |= fill_slab_row<K>(a_stage + seg * A_SLAB, swz, wsm_a, cols_hit, (R0 + seg) - Y0, e0, dirty,
+                                                  1u << (st * GS_ROWS + seg));
+                    if (wrote) fence_proxy_async_smem();
                     mbar_arrive(&a_full[st]);
                 }
             }
@@ -241,19 +246,26 @@ k_local_attn_bwd_gs_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                     const long long qofs = (long long)qy * W + qx;
                     float p[KK];
                     pixel_softmax_f32<KK>(logits + (long long)b * KK * hw + qofs, hw, p);
-                    const __nv_bfloat16* go = gout + ((long long)b * hw + qofs) * C + c0;
+                    // fire-and-forget vector reductions (red.global.add.noftz.bf16x2), lanes <-> channel pairs:
+                    // scalar bf16 atomics with a return value made one such pixel cost ~1 ms (a straggler CTA)
+                    const __nv_bfloat162* go2 = reinterpret_cast<const __nv_bfloat162*>(gout + ((long long)b * hw + qofs) * C + c0);
                     __nv_bfloat16* gs = gsrc + (long long)b * Hs * Ws * C + c0;
-                    for (int c = lane; c < CN; c += 32) {
-                        const float gv = __bfloat162float(go[c]) * (1.0f / static_cast<float>(KK));
+                    for (int c2 = lane; c2 < CN / 2; c2 += 32) {
+                        const float2 gv = __bfloat1622float2(go2[c2]);
+                        const float g0 = gv.x * (1.0f / static_cast<float>(KK)), g1 = gv.y * (1.0f / static_cast<float>(KK));
                         for (int i = 0; i < K; ++i) {
                             const AxisTap<float> ty = axis_tap<float>(qfy, i - K / 2, qy, Hs);
                             for (int j = 0; j < K; ++j) {
                                 const AxisTap<float> tx = axis_tap<float>(qfx, j - K / 2, qx, Ws);
-                                const float gp = gv * p[i * K + j];
-                                atomicAdd(gs + ((long long)ty.lo * Ws + tx.lo) * C + c, __float2bfloat16_rn(gp * tx.wlo * ty.wlo));
-                                atomicAdd(gs + ((long long)ty.lo * Ws + tx.hi) * C + c, __float2bfloat16_rn(gp * tx.whi * ty.wlo));
-                                atomicAdd(gs + ((long long)ty.hi * Ws + tx.lo) * C + c, __float2bfloat16_rn(gp * tx.wlo * ty.whi));
-                                atomicAdd(gs + ((long long)ty.hi * Ws + tx.hi) * C + c, __float2bfloat16_rn(gp * tx.whi * ty.whi));
+                                const float pij = p[i * K + j];
+                                const float w4[4] = {tx.wlo * ty.wlo, tx.whi * ty.wlo, tx.wlo * ty.whi, tx.whi * ty.whi};
+                                const long long o4[4] = {(long long)ty.lo * Ws + tx.lo, (long long)ty.lo * Ws + tx.hi,
+                                                         (long long)ty.hi * Ws + tx.lo, (long long)ty.hi * Ws + tx.hi};
+#pragma unroll
+                                for (int q4 = 0; q4 < 4; ++q4) {
+                                    const __nv_bfloat162 v2 = __floats2bfloat162_rn(g0 * pij * w4[q4], g1 * pij * w4[q4]);
+                                    red_add_bf16x2(gs + o4[q4] * C + 2 * c2, *reinterpret_cast<const uint32_t*>(&v2));
+                                }
                             }
                         }
                     }

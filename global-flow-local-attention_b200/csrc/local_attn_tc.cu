@@ -42,15 +42,21 @@ namespace gfla {
 namespace tc {
 
 constexpr int RCH = 2;                  // source rows per pipeline stage
-constexpr int NSTAGE = 8;
-constexpr int NINFO = 16;               // >= NSTAGE + 3 (producer run-ahead + 2 accumulators in flight)
+constexpr int NSTAGE = 4;                // stages of FBW x RCH positions
+constexpr int NINFO = 8;                 // >= NSTAGE + 3 (producer run-ahead + 2 accumulators in flight)
 constexpr int NTHREADS = 320;
 
-template <int CN>
+// Row-segment width: channels-last boxes start at any x, so one 32-wide segment usually spans the whole tap
+// footprint of a 16-pixel-wide group (half as many stages and slab rows as two 16-wide ones).  Planar (NCHW)
+// boxes must start on an 8-pixel boundary, where 16-wide segments waste less.
+template <bool NHWC> struct SegW { static constexpr int value = NHWC ? 32 : 16; };
+
+template <int CN, int FBW>
 struct Smem {
-    static constexpr int S_SLAB = CN * 32;                   // [CN channels][16 x] bf16
+    static constexpr int S_SLAB = CN * FBW * 2;              // one source row segment: [CN channels] x [FBW x] bf16
+    static constexpr int FA_SLAB = 128 * FBW * 2;            // weight slab: [128 pixels][FBW positions] bf16
     static constexpr int S_STAGE = RCH * S_SLAB;
-    static constexpr int A_STAGE = RCH * A_SLAB;
+    static constexpr int A_STAGE = RCH * FA_SLAB;
     static constexpr int OFF_S = 0;
     static constexpr int OFF_A = OFF_S + NSTAGE * S_STAGE;
     static constexpr int OFF_W = OFF_A + NSTAGE * A_STAGE;   // [36][128] bf16 collapsed windows
@@ -73,7 +79,8 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                     const float* __restrict__ flow, const __nv_bfloat16* __restrict__ logits,
                     __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ probs, int B, int C, int Hs, int Ws,
                     int H, int W, int prefetch_mode) {
-    using SM = Smem<CN>;
+    constexpr int FBW = SegW<NHWC>::value;
+    using SM = Smem<CN, FBW>;
     constexpr int K1 = K + 1, KK = K * K;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -131,19 +138,19 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                     for (int r = lane; r < prow; r += 32)
                         prefetch_l2_bulk(src + (((long long)bn * Hs + ny0 + r) * Ws + nx0) * C, bytes);
                 } else if ((prefetch_mode & 255) == 1) {
-                    const int pcb = (nx1 - nx0 + BW) / BW;
+                    const int pcb = (nx1 - nx0 + FBW) / FBW;
                     for (int idx = lane; idx < pcb * prow; idx += 32) {
                         const int cb = idx / prow, yy = ny0 + idx % prow;
                         if (NHWC) {
 #pragma unroll
-                            for (int cg = 0; cg < CN / 64; ++cg) tma_prefetch_4d(&tmap_src, c0 + cg * 64, nx0 + cb * BW, yy, bn);
+                            for (int cg = 0; cg < CN / 64; ++cg) tma_prefetch_4d(&tmap_src, c0 + cg * 64, nx0 + cb * FBW, yy, bn);
                         } else {
-                            tma_prefetch_4d(&tmap_src, nx0 + cb * BW, yy, c0, bn);
+                            tma_prefetch_4d(&tmap_src, nx0 + cb * FBW, yy, c0, bn);
                         }
                     }
                 }
             }
-            const int ncb = (xmax - xmin + BW) / BW, nrc = (ymax - ymin + RCH) / RCH;
+            const int ncb = (xmax - xmin + FBW) / FBW, nrc = (ymax - ymin + RCH) / RCH;
             if (lane == 0) {
                 infos[gi % NINFO] = GroupInfo{xmin, ymin, ncb, nrc};
                 mbar_arrive(&info_full[gi % NINFO]);
@@ -157,13 +164,13 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
 #pragma unroll
                         for (int rr = 0; rr < RCH; ++rr) {
                             uint8_t* dst = smem + SM::OFF_S + slot * SM::S_STAGE + rr * SM::S_SLAB;
-                            if (NHWC) {  // [CN/64 channel groups][16 x][64 channels]: one 2 KB box per channel group
+                            if (NHWC) {  // [CN/64 channel groups][FBW x][64 channels]: one box per channel group
 #pragma unroll
                                 for (int cg = 0; cg < CN / 64; ++cg)
-                                    tma_load_4d(dst + cg * 2048, &tmap_src, &full_s[slot], c0 + cg * 64, xmin + cb * BW,
+                                    tma_load_4d(dst + cg * (FBW * 128), &tmap_src, &full_s[slot], c0 + cg * 64, xmin + cb * FBW,
                                                 ymin + rc * RCH + rr, b);
-                            } else {     // [CN channels][16 x]
-                                tma_load_4d(dst, &tmap_src, &full_s[slot], xmin + cb * BW, ymin + rc * RCH + rr, c0, b);
+                            } else {     // [CN channels][FBW x]
+                                tma_load_4d(dst, &tmap_src, &full_s[slot], xmin + cb * FBW, ymin + rc * RCH + rr, c0, b);
                             }
                         }
                     }
@@ -192,14 +199,18 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                     const uint32_t a0 = smem_u32(smem + SM::OFF_A + slot * SM::A_STAGE);
                     const uint32_t b0 = smem_u32(smem + SM::OFF_S + slot * SM::S_STAGE);
 #pragma unroll
-                    for (int rr = 0; rr < RCH; ++rr) {
-                        const uint64_t ad = make_smem_desc(a0 + rr * A_SLAB, 16, 256, kSwizzle32);
-                        // NCHW: B = [CN rows][16 x], K-major, 32B swizzle.  NHWC: B = [16 x][64 ch] per channel group,
-                        // MN-major, 128B swizzle: LBO = next channel group (2 KB), SBO = next 8 positions (1 KB).
-                        const uint64_t bd = NHWC ? make_smem_desc(b0 + rr * SM::S_SLAB, 2048, 1024, kSwizzle128)
-                                                 : make_smem_desc(b0 + rr * SM::S_SLAB, 16, 256, kSwizzle32);
-                        umma_f16(d_tmem, ad, bd, idesc, (st | rr) != 0 ? 1u : 0u);
-                    }
+                    for (int rr = 0; rr < RCH; ++rr)
+#pragma unroll
+                        for (int h = 0; h < FBW / 16; ++h) {  // K = 16 positions per MMA
+                            // A = [128 px][FBW pos], K-major, rows of FBW*2 bytes with the matching swizzle; K-advance = +32 B
+                            const uint64_t ad = FBW == 32 ? make_smem_desc(a0 + rr * SM::FA_SLAB + h * 32, 16, 512, kSwizzle64)
+                                                          : make_smem_desc(a0 + rr * SM::FA_SLAB, 16, 256, kSwizzle32);
+                            // NCHW: B = [CN rows][16 x], K-major, 32B swizzle.  NHWC: B = [FBW x][64 ch] per channel group,
+                            // MN-major, 128B swizzle: LBO = next channel group, SBO = next 8 positions (1 KB); K-advance = 2 KB
+                            const uint64_t bd = NHWC ? make_smem_desc(b0 + rr * SM::S_SLAB + h * 2048, FBW * 128, 1024, kSwizzle128)
+                                                     : make_smem_desc(b0 + rr * SM::S_SLAB, 16, 256, kSwizzle32);
+                            umma_f16(d_tmem, ad, bd, idesc, (st | rr | h) != 0 ? 1u : 0u);
+                        }
                     tc_commit(&empty[slot]);
                     if (st == nst - 1) tc_commit(&acc_full[buf]);
                 }
@@ -211,9 +222,10 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
         const int q = warp & 3, m = q * 32 + lane;  // pixel index inside the group
         const float inv_kk = 1.0f / static_cast<float>(KK);
         const uint32_t wsm_a = smem_u32(smem + SM::OFF_W) + m * 4;      // [18 words][128 pixels] packed bf16x2 rows
-        const uint32_t a_base = smem_u32(smem + SM::OFF_A) + m * 32;    // this pixel's 32-byte row in slab 0
-        const uint32_t swz = ((m >> 2) & 1) << 4;                        // 32B swizzle: 16B chunk ^= bit 2 of the row
-        uint32_t it = 0;
+        const uint32_t a_base = smem_u32(smem + SM::OFF_A) + m * (FBW * 2);   // this pixel's row in slab 0
+        // swizzle XOR of the 16B chunks of this row: 32B rows -> bit 2 of the row index, 64B rows -> bits 1-2
+        const uint32_t swz = FBW == 32 ? (((m >> 1) & 3) << 4) : (((m >> 2) & 1) << 4);
+        uint32_t it = 0, dirty = 0xffffffffu;   // slab rows start with unknown contents: treat them as dirty
         int gi = 0;
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
             const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
@@ -242,17 +254,19 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             mbar_wait(&info_full[gi % NINFO], (gi / NINFO) & 1, 0x020500, gi);
             const GroupInfo inf = infos[gi % NINFO];
             for (int cb = 0; cb < inf.ncb; ++cb) {
-                const int e0 = X0 - (inf.x0 + cb * BW);            // box position of window column 0
-                const bool cols_hit = live && e0 > -K1 && e0 < BW;
+                const int e0 = X0 - (inf.x0 + cb * FBW);           // box position of window column 0
+                const bool cols_hit = live && e0 > -K1 && e0 < FBW;
                 for (int rc = 0; rc < inf.nrc; ++rc, ++it) {
                     const int slot = it % NSTAGE;
                     mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x020200 | slot, it);
                     const uint32_t a_stage = a_base + slot * SM::A_STAGE;
                     const int R0 = inf.y0 + rc * RCH;
+                    bool wrote = false;
 #pragma unroll
                     for (int rr = 0; rr < RCH; ++rr)
-                        fill_slab_row<K>(a_stage + rr * A_SLAB, swz, wsm_a, cols_hit, (R0 + rr) - Y0, e0);
-                    fence_proxy_async_smem();
+                        wrote |= fill_slab_row<K, FBW>(a_stage + rr * SM::FA_SLAB, swz, wsm_a, cols_hit, (R0 + rr) - Y0, e0, dirty,
+                                                  1u << (slot * RCH + rr));
+                    if (wrote) fence_proxy_async_smem();
                     mbar_arrive(&full_a[slot]);
                 }
             }
@@ -364,25 +378,25 @@ static int launch_tc(const void* src, const void* flow, const void* logits, void
     if (NHWC) {  // (c, x, y, b), box [64 c][16 x]: 128-byte runs, 128B swizzle
         const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)B};
         const cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)Ws * C * 2, (cuuint64_t)Hs * Ws * C * 2};
-        const cuuint32_t box[4] = {64, BW, 1, 1};
+        const cuuint32_t box[4] = {64, SegW<true>::value, 1, 1};
         r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), gdim, gstr, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {     // (x, y, c, b), box [CN c][16 x]: 32-byte runs, 32B swizzle
         const cuuint64_t gdim[4] = {(cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)C, (cuuint64_t)B};
         const cuuint64_t gstr[3] = {(cuuint64_t)Ws * 2, (cuuint64_t)Hs * Ws * 2, (cuuint64_t)C * Hs * Ws * 2};
-        const cuuint32_t box[4] = {BW, 1, CN, 1};
+        const cuuint32_t box[4] = {SegW<false>::value, 1, CN, 1};
         r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), gdim, gstr, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) return GFLA_E_NOTSUP;
     auto kern = k_local_attn_fwd_tc<K, CN, NHWC>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<CN>::ALLOC);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<CN, SegW<NHWC>::value>::ALLOC);
     if (e != cudaSuccess) return static_cast<int>(e);
     const int ngroups = B * ((H + GH - 1) / GH) * ((W + GW - 1) / GW);
     dim3 grid((unsigned)min(ngroups, sm_count()), (unsigned)(C / CN));
-    kern<<<grid, NTHREADS, Smem<CN>::ALLOC, st_>>>(tmap, (const __nv_bfloat16*)src, (const float*)flow,
+    kern<<<grid, NTHREADS, Smem<CN, SegW<NHWC>::value>::ALLOC, st_>>>(tmap, (const __nv_bfloat16*)src, (const float*)flow,
                                                    (const __nv_bfloat16*)logits, (__nv_bfloat16*)out,
                                                    (__nv_bfloat16*)probs, B, C, Hs, Ws, H, W, tune_knob("GFLA_TC_PREFETCH", 0));
     return launch_status();

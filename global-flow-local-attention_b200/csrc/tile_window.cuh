@@ -151,24 +151,33 @@ __device__ __forceinline__ void store_window_words(uint32_t wsm_a, const float* 
 
 // One 32-byte slab row (this pixel x 16 positions of one source row segment): zero it, then drop in the
 // window row r (if the segment holds any of its K+1 columns).  e0 = box position of window column 0.
-template <int K>
-__device__ __forceinline__ void fill_slab_row(uint32_t row, uint32_t swz, uint32_t wsm_a, bool hit, int r, int e0) {
+// `dirty` remembers (one bit per slab row of the ring, kept by the owning thread) whether the row currently
+// holds non-zero weights: rows that are still all-zero from their last use are not rewritten.
+// Returns true if anything was stored (the caller then needs the async-proxy fence).
+template <int K, int BWT = BW>
+__device__ __forceinline__ bool fill_slab_row(uint32_t row, uint32_t swz, uint32_t wsm_a, bool hit, int r, int e0,
+                                              uint32_t& dirty, uint32_t bit) {
     constexpr int K1 = K + 1;
-    sts128(row, 0u, 0u, 0u, 0u);
-    sts128(row + 16, 0u, 0u, 0u, 0u);
-    if (hit && r >= 0 && r <= K) {
+    const bool write = hit && r >= 0 && r <= K;
+    if (!write && !(dirty & bit)) return false;
+#pragma unroll
+    for (int ch = 0; ch < BWT / 8; ++ch) sts128(row + ch * 16, 0u, 0u, 0u, 0u);
+    dirty &= ~bit;
+    if (write) {
+        dirty |= bit;
         uint32_t wv[K1 / 2];
 #pragma unroll
         for (int q = 0; q < K1 / 2; ++q) wv[q] = lds32(wsm_a + (r * (K1 / 2) + q) * 512);
 #pragma unroll
         for (int c = 0; c < K1; ++c) {
             const int e = e0 + c;
-            if (e >= 0 && e < BW) {
+            if (e >= 0 && e < BWT) {
                 const uint32_t half = (c & 1) ? (wv[c >> 1] >> 16) : (wv[c >> 1] & 0xffffu);
-                sts16(row + ((((e >> 3) << 4) ^ swz)) + (e & 7) * 2, half);
+                sts16(row + ((((e >> 3) << 4) ^ swz)) + (e & 7) * 2, half);   // swz = swizzle XOR of this row's 16B chunks
             }
         }
     }
+    return true;
 }
 
 // tuning knobs (environment, read per launch)
