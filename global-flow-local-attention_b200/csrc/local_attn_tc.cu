@@ -233,7 +233,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             const bool valid = px < W && py < H;
             int X0 = 0, Y0 = 0;
             bool live = false;
-            if (valid) {
+            if (valid && !(prefetch_mode & 512)) {   // bit 9: timing experiment, skip the per-pixel window construction
                 const long long pofs = (long long)py * W + px;
                 float p[KK];
                 pixel_softmax_f32<KK>(logits + (long long)b * KK * hw + pofs, hw, p);
@@ -255,7 +255,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             const GroupInfo inf = infos[gi % NINFO];
             for (int cb = 0; cb < inf.ncb; ++cb) {
                 const int e0 = X0 - (inf.x0 + cb * FBW);           // box position of window column 0
-                const bool cols_hit = live && e0 > -K1 && e0 < FBW;
+                const bool cols_hit = live && e0 > -K1 && e0 < FBW && !(prefetch_mode & 1024);   // bit 10: timing experiment
                 for (int rc = 0; rc < inf.nrc; ++rc, ++it) {
                     const int slot = it % NSTAGE;
                     mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x020200 | slot, it);
