@@ -8,7 +8,8 @@ unchanged; what changes is how ``forward`` runs:
     reference                                   here
     ---------                                   ----
     block_source = extractor(source, flow)      same (needed as conv input)
-    block_target = extractor(target, 0)         same
+    block_target = extractor(target, 0)         NOT materialised: its conv == a stride-1 conv of `target`
+                                                with replicate padding (see _logits)
     attn = fc(cat(block_target, block_source))  conv -> act -> conv produce LOGITS;
            ... ending in Softmax(dim=1)         the softmax is folded into the fused kernel
     attn = reshape(attn, k)                     --
@@ -17,6 +18,7 @@ unchanged; what changes is how ``forward`` runs:
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 from torch.autograd import Function
 
 from . import functional as F_
@@ -75,10 +77,21 @@ class ExtractorAttn(nn.Module):
             softmax,)
 
     def _logits(self, source, target, flow_field):
+        """conv(k, stride k) over cat(block_target, block_source), then act, then the 1x1 conv (no softmax).
+
+        The target half never needs its block tensor: BlockExtractor with a zero flow copies, for output
+        position (y*k+i, x*k+j), target[clamp(y+i-k//2), clamp(x+j-k//2)] (integer taps: weights 1 and 0,
+        block_extractor_kernel.cu:62-82), so a kernel-k stride-k convolution over it IS an ordinary kernel-k
+        stride-1 convolution of `target` with replicate padding (k//2 before, k-1-k//2 after) using the first
+        C input channels of the same weight.  Only block_source (flow-dependent, bilinear) is materialised.
+        """
+        conv1 = self.fully_connect_layer[0]
+        k, c = self.kernel_size, source.shape[1]
         block_source = self.extractor(source, flow_field)
-        block_target = self.extractor(target, torch.zeros_like(flow_field))
-        x = torch.cat((block_target, block_source), 1)
-        for layer in list(self.fully_connect_layer)[:-1]:      # everything up to (not including) the softmax
+        x = F.conv2d(block_source, conv1.weight[:, c:], None, stride=k)
+        lo, hi = k // 2, k - 1 - k // 2
+        x = x + F.conv2d(F.pad(target, (lo, hi, lo, hi), mode="replicate"), conv1.weight[:, :c], conv1.bias)
+        for layer in list(self.fully_connect_layer)[1:-1]:      # nonlinearity, 1x1 conv; not the softmax
             x = layer(x)
         return x, block_source
 
