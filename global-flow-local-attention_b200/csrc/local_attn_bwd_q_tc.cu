@@ -24,7 +24,7 @@ namespace gfla {
 namespace tc {
 
 constexpr int Q_ROWS = 4;          // source rows per stage: N = 4 x 16 = 64 positions
-constexpr int Q_NS = 3;            // source-row stages
+constexpr int Q_NS = 4;            // source-row stages (64 KB grad_out tile + 4 x 32 KB)
 constexpr int Q_NACC = 4;          // accumulator buffers of 64 TMEM columns
 constexpr int Q_NINFO = 8;
 constexpr int Q_NTHREADS = 192;

@@ -310,7 +310,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                             __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
                             pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
                             pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                            o4[i] = pk;
+                            __stcs(o4 + i, pk);   // streaming store: written once, never re-read by this kernel
                         }
                     } else {
 #pragma unroll

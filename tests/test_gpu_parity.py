@@ -557,3 +557,31 @@ def test_local_attn_bwd_nchw_bf16_routes_through_tile_kernels(F_, oracle_lib):
     np.testing.assert_allclose(host(gs), ogs, rtol=0, atol=1e-2 * max(1.0, float(np.abs(ogs).max())))
     np.testing.assert_allclose(host(gl), ogl, rtol=0, atol=1e-2)
     np.testing.assert_allclose(host(gf), ogf, rtol=2e-2, atol=2e-2 * max(1.0, float(np.abs(ogf).max())))
+
+
+def test_cfg2_backward_tile_equals_cuda_core_backward(F_):
+    """one full-size cfg2 sample (C=256, 256x256, k=5, bf16 channels_last): the three tensor-core backward
+    kernels agree with the (oracle-checked) CUDA-core backward; also exercises > 50 groups per CTA."""
+    torch.manual_seed(4)
+    B, C, H, W, k = 1, 256, 256, 256, 5
+    cl = torch.channels_last
+    s = torch.randn(B, C, H, W, device=DEV).bfloat16().contiguous(memory_format=cl)
+    g = torch.randn(B, C, H, W, device=DEV).bfloat16().contiguous(memory_format=cl)
+    f = _smooth_flow_t(B, H, W)
+    l = torch.randn(B, k * k, H, W, device=DEV).bfloat16()
+    gs, gf, gl = F_.local_attn_bwd(s, f, l, g, k, algo="tile")
+    # reference: fp32 CUDA-core kernels on the same (bf16-rounded) values: fp32 atomics, fp32 accumulation
+    rs, rf, rl = F_.local_attn_bwd(s.float().contiguous(), f, l.float(), g.float().contiguous(), k, algo="gather")
+    assert (gs.float() - rs).abs().max().item() <= 1e-2 * max(1.0, rs.abs().max().item())
+    assert (gl.float() - rl).abs().max().item() <= 1e-2
+    assert (gf - rf).abs().max().item() <= 2e-2 * max(1.0, rf.abs().max().item())
+
+
+def test_tile_kernels_many_groups_small_grid(F_, oracle_lib):
+    """more pixel groups per CTA than the info ring has slots, ragged last group: B=3, 40x72 (C=64)"""
+    B, C, H, W, k = 3, 64, 40, 72, 3
+    s, f, l = _tile_inputs(B, C, H, W, H, W, k, "smooth", seed=5)
+    s = s.contiguous(memory_format=torch.channels_last)
+    out = F_.local_attn_fwd(s, f, l, k, algo="tile")
+    ref = oracle_lib.local_attn_fwd(host(s), f.cpu().numpy(), host(l), k)
+    np.testing.assert_allclose(host(out), ref, rtol=0, atol=1e-2)
