@@ -261,6 +261,28 @@ def main():
     ms_per_step = total_ms / steps
     value = world * B * H * W / (ms_per_step * 1e-3) / 1e6
 
+    # ---- the same step with planar (contiguous NCHW) feature tensors, for callers that keep the reference's layout:
+    #      forward = NCHW variant of the tile kernel, backward = re-layout + channels-last tile kernels + re-layout
+    nchw = None
+    if args.layout == "nhwc":
+        src_p, gout_p = src.contiguous(), gout.contiguous()
+        def step_planar():
+            F_.local_attn_fwd(src_p, flow, logits, k, algo=args.algo)
+            F_.local_attn_bwd(src_p, flow, logits, gout_p, k)
+        for _ in range(2):
+            step_planar()
+        barrier()
+        a_, b__ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        for _ in range(3):
+            step_planar()
+        b__.record()
+        barrier()
+        p_ms = reduce_max_time(a_.elapsed_time(b__), dev) / 3
+        nchw = {"value": world * B * H * W / (p_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": p_ms, "steps": 3,
+                "note": "contiguous NCHW feature tensors (the reference's layout), same workload"}
+        del src_p, gout_p
+
     # ---- e2e: public autograd API, host buffers, copies inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -342,6 +364,7 @@ def main():
             "roofline": dominant, "roofline_fwd": rf_fwd, "roofline_bwd": rf_bwd,
             "step_roofline_frac": (fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9 / peak,
             "clocks": sampler.summary(t_wall0, t_wall1),
+            "planar_nchw": nchw,
             "gpu_launches": 4 * steps,   # fwd tile + grad_source tile + grad_flow/logits tile + memset node
             "e2e": e2e}
     if world == 1 and not args.no_cpu_baseline:

@@ -16,6 +16,7 @@ bool local_attn_bwd_q_tc_supported(int C, int k);
 int local_attn_bwd_q_tc(const void* src, const void* flow, const void* logits, const void* gout, void* gflow, void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate, cudaStream_t);
 int local_attn_bwd_gs_tc(const void* flow, const void* logits, const void* gout, void* gsrc, int B, int C, int Hs, int Ws, int H, int W, int k, cudaStream_t);
 int local_attn_fwd_tc(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int relayout(const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int tc_debug_set_buffer(void*);
 int tc_debug_set_buffer_bwd(void*);
 bool local_attn_fwd_tc_supported(int B, int C, int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, int layout, const void* src, const void* out);
@@ -57,6 +58,15 @@ int gfla_device_check(void) {
 int gfla_debug_set_buffer(void* host_mapped_u64x8) {
     const int e = tc_debug_set_buffer(host_mapped_u64x8);
     return e ? e : tc_debug_set_buffer_bwd(host_mapped_u64x8);
+}
+
+int gfla_relayout(const void* src, void* dst, int B, int C, int H, int W, int dtype, int to_nhwc, gfla_stream_t stream) {
+    REQ_PTR(src); REQ_PTR(dst);
+    if (!pos(B) || !pos(C) || !pos(H) || !pos(W)) return GFLA_E_SHAPE;
+    if (!dtype_known(dtype)) return GFLA_E_DTYPE;
+    if (src == dst) return GFLA_E_NOTSUP;
+    REQ_ALIGN(src, dtype); REQ_ALIGN(dst, dtype);
+    return relayout(src, dst, B, C, H, W, dtype, to_nhwc, (cudaStream_t)stream);
 }
 
 int gfla_block_extract_fwd(const void* source, const void* flow, void* out, int B, int C, int Hs, int Ws, int Hf,

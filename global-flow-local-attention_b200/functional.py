@@ -170,6 +170,22 @@ def local_attn_fwd(source, flow, logits, k, return_probs=False, algo="auto"):
     return (out, probs) if return_probs else out
 
 
+def relayout(t: torch.Tensor, to_channels_last: bool) -> torch.Tensor:
+    """Out-of-place NCHW <-> channels_last copy of a [B,C,H,W] tensor with the library's own transpose kernel."""
+    _need_cuda(t)
+    b, c, h, w = t.shape
+    if to_channels_last:
+        assert t.is_contiguous()
+        out = torch.empty((b, c, h, w), dtype=t.dtype, device=t.device, memory_format=torch.channels_last)
+    else:
+        assert t.is_contiguous(memory_format=torch.channels_last)
+        out = torch.empty((b, c, h, w), dtype=t.dtype, device=t.device)
+    with torch.cuda.device_of(t):
+        _lib.check(_lib.lib().gfla_relayout(_p(t), _p(out), b, c, h, w, _dt(t), 1 if to_channels_last else 0, _stream(t)),
+                   "relayout")
+    return out
+
+
 def _tile_bwd_eligible(source, flow, k) -> bool:
     """what the backward tile kernels serve (mirrors local_attn_bwd_tc_supported in csrc/local_attn_bwd_tc.cu)"""
     c = source.shape[1]
@@ -185,9 +201,9 @@ def local_attn_bwd(source, flow, logits, grad_out, k, algo="auto"):
         # The backward tile kernels are channels-last only (every operand must be channel-contiguous for TMA).
         # For planar callers, re-lay the two feature tensors (two extra passes over them) instead of falling
         # back to the scalar-atomics kernel: ~100x faster at cfg2.
-        gs, gf, gl = local_attn_bwd(source.contiguous(memory_format=torch.channels_last), flow, logits,
-                                    grad_out.contiguous(memory_format=torch.channels_last), k, algo="auto")
-        return gs.contiguous(), gf, gl
+        go = grad_out if grad_out.is_contiguous() else grad_out.contiguous()
+        gs, gf, gl = local_attn_bwd(relayout(source, True), flow, logits, relayout(go, True), k, algo="auto")
+        return relayout(gs, False), gf, gl
     fmt = torch.channels_last if layout == _lib.GFLA_NHWC else torch.contiguous_format
     grad_out = grad_out.contiguous(memory_format=fmt)
     bs, ds, hs, ws = source.size()

@@ -76,6 +76,12 @@ int gfla_device_check(void);
  * traps instead of hanging the GPU.  Not used on the normal path. */
 int gfla_debug_set_buffer(void* host_mapped_u64x8);
 
+/* Re-layout of a [B,C,H,W] feature tensor between planar NCHW and channels-last NHWC storage
+ * (out of place; to_nhwc = 1: NCHW -> NHWC, 0: NHWC -> NCHW).  Not part of the reference's API: the
+ * Python layer uses it to serve planar bf16 callers with the channels-last tile kernels. */
+int gfla_relayout(const void* src, void* dst, int B, int C, int H, int W, int dtype, int to_nhwc,
+                  gfla_stream_t stream);
+
 /* ------------------------------------------------------------------------ *
  * block_extractor
  *   replaces block_extractor_cuda.forward(source, flow_field, output, k)

@@ -585,3 +585,13 @@ def test_tile_kernels_many_groups_small_grid(F_, oracle_lib):
     out = F_.local_attn_fwd(s, f, l, k, algo="tile")
     ref = oracle_lib.local_attn_fwd(host(s), f.cpu().numpy(), host(l), k)
     np.testing.assert_allclose(host(out), ref, rtol=0, atol=1e-2)
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32, torch.float64])
+def test_relayout_roundtrip(F_, dt):
+    torch.manual_seed(0)
+    x = torch.randn(3, 70, 13, 9, device=DEV).to(dt)
+    y = F_.relayout(x, True)
+    assert y.is_contiguous(memory_format=torch.channels_last) and torch.equal(y, x)
+    z = F_.relayout(y, False)
+    assert z.is_contiguous() and torch.equal(z, x)
