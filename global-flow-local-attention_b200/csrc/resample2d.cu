@@ -111,7 +111,8 @@ k_resample2d_fwd(const A* __restrict__ in1, const A* __restrict__ in2, A* __rest
     const int c0 = blockIdx.y * c_per_slice, c1 = min(C, c0 + c_per_slice);
     const A* s = in1 + ((long long)b * C + c0) * ipl;
     A* o = out + ((long long)b * C + c0) * opl + (long long)y * W + x;
-    for (int c = c0; c < c1; ++c, s += ipl, o += opl) {
+#pragma unroll 4
+    for (int c = c0; c < c1; ++c, s += ipl, o += opl) {   // unrolled: 4 channels x taps of independent loads in flight
         A val = static_cast<A>(0);
 #pragma unroll
         for (int q = 0; q < NT * NT * 4; ++q) val += w[q] * s[t.off[q]];
@@ -143,6 +144,7 @@ k_resample2d_bwd_in1(const A* __restrict__ in2, const A* __restrict__ gout, A* _
     const int c0 = blockIdx.y * c_per_slice, c1 = min(C, c0 + c_per_slice);
     A* gi = gin1 + ((long long)b * C + c0) * ipl;
     const A* go = gout + ((long long)b * C + c0) * opl + (long long)y * W + x;
+#pragma unroll 4
     for (int c = c0; c < c1; ++c, gi += ipl, go += opl) {
         const double g = static_cast<double>(*go);
 #pragma unroll
@@ -168,6 +170,7 @@ k_resample2d_bwd_in2(const A* __restrict__ in1, const A* __restrict__ in2, const
     const long long ipl = (long long)Hi * Wi, opl = (long long)H * W;
     const A* s = in1 + (long long)b * C * ipl;
     const A* go = gout + (long long)b * C * opl + (long long)y * W + x;
+#pragma unroll 4
     for (int c = 0; c < C; ++c, s += ipl, go += opl) {
         const A g = *go;
 #pragma unroll
