@@ -369,7 +369,8 @@ def main():
             "step_roofline_frac": (fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9 / peak,
             "clocks": sampler.summary(t_wall0, t_wall1),
             "planar_nchw": nchw,
-            "gpu_launches": 4 * steps,   # fwd tile + grad_source tile + grad_flow/logits tile + memset node
+            "gpu_launches": 3 * steps,   # our kernels per step: forward tile, grad_source tile, grad_flow/logits tile
+                                         # (plus one cudaMemsetAsync node for grad_source, not counted)
             "e2e": e2e}
     if world == 1 and not args.no_cpu_baseline:
         try:
