@@ -9,13 +9,13 @@ int attn_reshape_fwd(const void*, void*, int, int, int, int, int, cudaStream_t);
 int attn_reshape_bwd(const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int resample2d_fwd(const void*, const void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int resample2d_bwd(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
-int local_attn_fwd_gather(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int local_attn_fwd_gather(const void*, const void*, const void*, void*, void*, const void*, const void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int local_attn_bwd_gather(const void*, const void*, const void*, const void*, void*, void*, void*, int, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 bool local_attn_bwd_tc_supported(int C, int k, int dtype, int flow_dtype, int layout, const void* gout, const void* gsrc);
 bool local_attn_bwd_q_tc_supported(int C, int k);
 int local_attn_bwd_q_tc(const void* src, const void* flow, const void* logits, const void* gout, void* gflow, void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate, cudaStream_t);
 int local_attn_bwd_gs_tc(const void* flow, const void* logits, const void* gout, void* gsrc, int B, int C, int Hs, int Ws, int H, int W, int k, cudaStream_t);
-int local_attn_fwd_tc(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int local_attn_fwd_tc(const void*, const void*, const void*, void*, void*, const void*, const void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int relayout(const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int tc_debug_set_buffer(void*);
 int tc_debug_set_buffer_bwd(void*);
@@ -127,9 +127,9 @@ int gfla_resample2d_bwd(const void* in1, const void* in2, const void* grad_out, 
                           (cudaStream_t)stream);
 }
 
-int gfla_local_attn_fwd(const void* source, const void* flow, const void* logits, void* out, void* probs, int B, int C,
-                        int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, int layout, int algo,
-                        gfla_stream_t stream) {
+static int local_attn_fwd_any(const void* source, const void* flow, const void* logits, void* out, void* probs,
+                              const void* prev, const void* mask, int B, int C, int Hs, int Ws, int H, int W, int k, int dtype,
+                              int flow_dtype, int layout, int algo, gfla_stream_t stream) {
     REQ_PTR(source); REQ_PTR(flow); REQ_PTR(logits); REQ_PTR(out);
     if (layout != GFLA_NCHW && layout != GFLA_NHWC) return GFLA_E_SHAPE;
     if (!pos(B) || !pos(C) || !pos(Hs) || !pos(Ws) || !pos(H) || !pos(W) || k < 1 || k > 9) return GFLA_E_SHAPE;
@@ -137,11 +137,28 @@ int gfla_local_attn_fwd(const void* source, const void* flow, const void* logits
     if (algo < 0 || algo > 2) return GFLA_E_NOTSUP;
     REQ_ALIGN(source, dtype); REQ_ALIGN(logits, dtype); REQ_ALIGN(out, dtype); REQ_ALIGN(flow, flow_dtype);
     if (probs) REQ_ALIGN(probs, dtype);
-    const bool tc_ok = local_attn_fwd_tc_supported(B, C, Hs, Ws, H, W, k, dtype, flow_dtype, layout, source, out);
+    if (prev) { REQ_ALIGN(prev, dtype); REQ_ALIGN(mask, dtype); }
+    const bool tc_ok = local_attn_fwd_tc_supported(B, C, Hs, Ws, H, W, k, dtype, flow_dtype, layout, source, out) &&
+                       (prev == nullptr || layout == GFLA_NCHW || aligned(prev, 16));
     if (algo == 2 && !tc_ok) return GFLA_E_NOTSUP;
     if (algo == 2 || (algo == 0 && tc_ok))
-        return local_attn_fwd_tc(source, flow, logits, out, probs, B, C, Hs, Ws, H, W, k, dtype, flow_dtype, layout, (cudaStream_t)stream);
-    return local_attn_fwd_gather(source, flow, logits, out, probs, B, C, Hs, Ws, H, W, k, dtype, flow_dtype, layout, (cudaStream_t)stream);
+        return local_attn_fwd_tc(source, flow, logits, out, probs, prev, mask, B, C, Hs, Ws, H, W, k, dtype, flow_dtype, layout, (cudaStream_t)stream);
+    return local_attn_fwd_gather(source, flow, logits, out, probs, prev, mask, B, C, Hs, Ws, H, W, k, dtype, flow_dtype, layout, (cudaStream_t)stream);
+}
+
+int gfla_local_attn_fwd(const void* source, const void* flow, const void* logits, void* out, void* probs, int B, int C,
+                        int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, int layout, int algo,
+                        gfla_stream_t stream) {
+    return local_attn_fwd_any(source, flow, logits, out, probs, nullptr, nullptr, B, C, Hs, Ws, H, W, k, dtype, flow_dtype,
+                              layout, algo, stream);
+}
+
+int gfla_local_attn_blend_fwd(const void* source, const void* flow, const void* logits, const void* prev, const void* mask,
+                              void* out, int B, int C, int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype,
+                              int layout, int algo, gfla_stream_t stream) {
+    REQ_PTR(prev); REQ_PTR(mask);
+    return local_attn_fwd_any(source, flow, logits, out, nullptr, prev, mask, B, C, Hs, Ws, H, W, k, dtype, flow_dtype, layout,
+                              algo, stream);
 }
 
 int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits, const void* grad_out,

@@ -55,8 +55,8 @@ __device__ __forceinline__ void pixel_softmax(const T* __restrict__ lg, long lon
 template <typename T, typename TF, int K>  // K = 0: run-time k (literal path only)
 __global__ void __launch_bounds__(128)
 k_local_attn_fwd(const T* __restrict__ src, const TF* __restrict__ flow, const T* __restrict__ logits,
-                 T* __restrict__ out, T* __restrict__ probs, int B, int C, int Hs, int Ws, int H, int W, int k_rt,
-                 int c_per_slice, int nhwc) {
+                 T* __restrict__ out, T* __restrict__ probs, const T* __restrict__ prev, const T* __restrict__ mask, int B,
+                 int C, int Hs, int Ws, int H, int W, int k_rt, int c_per_slice, int nhwc) {
     using A = typename Acc<T>::type;
     const int k = K ? K : k_rt, KK = k * k;
     const long long hw = (long long)H * W, total = (long long)B * hw;
@@ -81,6 +81,9 @@ k_local_attn_fwd(const T* __restrict__ src, const TF* __restrict__ flow, const T
     const T* s = src + (long long)b * C * spl + c0 * sc;
     T* o = out + (long long)b * C * hw + c0 * oc + pofs * (nhwc ? C : 1);
     const A inv_kk = static_cast<A>(1) / static_cast<A>(KK);
+    // optional fused mask blend (generator.py:130): out = prev * (1 - mask) + attention * mask
+    const T* pv = prev ? prev + (long long)b * C * hw + c0 * oc + pofs * (nhwc ? C : 1) : nullptr;
+    const A mk = prev ? static_cast<A>(ld(mask + (long long)b * hw + pofs)) : static_cast<A>(1);
 
     bool regular = false;
     if (K > 0) {
@@ -120,7 +123,9 @@ k_local_attn_fwd(const T* __restrict__ src, const TF* __restrict__ flow, const T
                 for (int r = 0; r < K1; ++r)
 #pragma unroll
                     for (int q = 0; q < K1; ++q) acc += Wc[r * K1 + q] * ld(s + cy[r] + cx[q]);
-                st(o, acc * inv_kk);
+                acc *= inv_kk;
+                if (pv) { acc = static_cast<A>(ld(pv)) * (static_cast<A>(1) - mk) + acc * mk; pv += oc; }
+                st(o, acc);
             }
         }
     }
@@ -139,7 +144,9 @@ k_local_attn_fwd(const T* __restrict__ src, const TF* __restrict__ flow, const T
                     acc += p[i * k + j] * v;
                 }
             }
-            st(o, acc * inv_kk);
+            acc *= inv_kk;
+            if (pv) { acc = static_cast<A>(ld(pv)) * (static_cast<A>(1) - mk) + acc * mk; pv += oc; }
+            st(o, acc);
         }
     }
 }
@@ -281,13 +288,13 @@ k_local_attn_bwd(const T* __restrict__ src, const TF* __restrict__ flow, const T
 }
 
 template <typename T, typename TF, int K>
-static int la_launch_fwd(const void* src, const void* flow, const void* logits, void* out, void* probs, int B, int C,
-                         int Hs, int Ws, int H, int W, int k, int nhwc, cudaStream_t st_) {
+static int la_launch_fwd(const void* src, const void* flow, const void* logits, void* out, void* probs, const void* prev,
+                         const void* mask, int B, int C, int Hs, int Ws, int H, int W, int k, int nhwc, cudaStream_t st_) {
     const long long total = (long long)B * H * W;
     const int threads = 128, slices0 = channel_splits(total, C, threads), cps = (C + slices0 - 1) / slices0;
     dim3 grid((unsigned)((total + threads - 1) / threads), (unsigned)((C + cps - 1) / cps));
     k_local_attn_fwd<T, TF, K><<<grid, threads, 0, st_>>>((const T*)src, (const TF*)flow, (const T*)logits, (T*)out,
-                                                         (T*)probs, B, C, Hs, Ws, H, W, k, cps, nhwc);
+                                                         (T*)probs, (const T*)prev, (const T*)mask, B, C, Hs, Ws, H, W, k, cps, nhwc);
     return launch_status();
 }
 
@@ -313,9 +320,9 @@ static int la_launch_bwd(const void* src, const void* flow, const void* logits, 
     }
 
 template <typename T, typename TF>
-static int la_fwd_k(const void* src, const void* flow, const void* logits, void* out, void* probs, int B, int C, int Hs,
-                    int Ws, int H, int W, int k, int nhwc, cudaStream_t st_) {
-    GFLA_K_DISPATCH(la_launch_fwd, src, flow, logits, out, probs, B, C, Hs, Ws, H, W, k, nhwc, st_)
+static int la_fwd_k(const void* src, const void* flow, const void* logits, void* out, void* probs, const void* prev,
+                    const void* mask, int B, int C, int Hs, int Ws, int H, int W, int k, int nhwc, cudaStream_t st_) {
+    GFLA_K_DISPATCH(la_launch_fwd, src, flow, logits, out, probs, prev, mask, B, C, Hs, Ws, H, W, k, nhwc, st_)
 }
 template <typename T, typename TF>
 static int la_bwd_k(const void* src, const void* flow, const void* logits, const void* gout, void* gsrc, void* gflow,
@@ -324,12 +331,13 @@ static int la_bwd_k(const void* src, const void* flow, const void* logits, const
     GFLA_K_DISPATCH(la_launch_bwd, src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, k, accumulate, nhwc, do_gs, st_)
 }
 
-int local_attn_fwd_gather(const void* src, const void* flow, const void* logits, void* out, void* probs, int B, int C,
-                          int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, int layout, cudaStream_t st_) {
+int local_attn_fwd_gather(const void* src, const void* flow, const void* logits, void* out, void* probs, const void* prev,
+                          const void* mask, int B, int C, int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype,
+                          int layout, cudaStream_t st_) {
     const int nhwc = layout == GFLA_NHWC;
     return GFLA_DISPATCH_T(dtype, [&]() -> int {
-        if (flow_dtype == dtype) return la_fwd_k<T, T>(src, flow, logits, out, probs, B, C, Hs, Ws, H, W, k, nhwc, st_);
-        return la_fwd_k<T, float>(src, flow, logits, out, probs, B, C, Hs, Ws, H, W, k, nhwc, st_);
+        if (flow_dtype == dtype) return la_fwd_k<T, T>(src, flow, logits, out, probs, prev, mask, B, C, Hs, Ws, H, W, k, nhwc, st_);
+        return la_fwd_k<T, float>(src, flow, logits, out, probs, prev, mask, B, C, Hs, Ws, H, W, k, nhwc, st_);
     });
 }
 

@@ -77,8 +77,9 @@ template <int K, int CN, bool NHWC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfloat16* __restrict__ src,
                     const float* __restrict__ flow, const __nv_bfloat16* __restrict__ logits,
-                    __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ probs, int B, int C, int Hs, int Ws,
-                    int H, int W, int prefetch_mode) {
+                    __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ probs,
+                    const __nv_bfloat16* __restrict__ prev, const __nv_bfloat16* __restrict__ mask, int B, int C, int Hs,
+                    int Ws, int H, int W, int prefetch_mode) {
     constexpr int FBW = SegW<NHWC>::value;
     using SM = Smem<CN, FBW>;
     constexpr int K1 = K + 1, KK = K * K;
@@ -293,12 +294,36 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * CN;
             __nv_bfloat16* o = NHWC ? out + ((long long)b * hw + pofs) * C + c0 : out + ((long long)b * C + c0) * hw + pofs;
+            // optional fused mask blend (generator.py:130): out = prev * (1 - mask) + attention * mask
+            const __nv_bfloat16* pv = prev == nullptr ? nullptr
+                                      : (NHWC ? prev + ((long long)b * hw + pofs) * C + c0 : prev + ((long long)b * C + c0) * hw + pofs);
+            const float mk = (prev != nullptr && valid) ? __bfloat162float(mask[(long long)b * hw + pofs]) : 1.f;
 #pragma unroll 1
             for (int cc = 0; cc < CN / 32; ++cc) {
                 uint32_t v[32];
                 tmem_ld_32x32(taddr + cc * 32, v);
                 tmem_ld_wait();
                 if (valid && regular && !(prefetch_mode & 256)) {   // bit 8: debug knob, skip the stores
+                    if (pv != nullptr) {   // blend in fp32 before the single rounding to bf16
+                        if (NHWC) {
+                            const uint4* p4 = reinterpret_cast<const uint4*>(pv + cc * 32);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const uint4 pq = p4[i];
+                                const uint32_t pw[4] = {pq.x, pq.y, pq.z, pq.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pw[j]));
+                                    v[8 * i + 2 * j] = __float_as_uint(pf.x * (1.f - mk) + __uint_as_float(v[8 * i + 2 * j]) * mk);
+                                    v[8 * i + 2 * j + 1] = __float_as_uint(pf.y * (1.f - mk) + __uint_as_float(v[8 * i + 2 * j + 1]) * mk);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                v[i] = __float_as_uint(__bfloat162float(pv[(long long)(cc * 32 + i) * hw]) * (1.f - mk) + __uint_as_float(v[i]) * mk);
+                        }
+                    }
                     if (NHWC) {
                         uint4* o4 = reinterpret_cast<uint4*>(o + cc * 32);
 #pragma unroll
@@ -357,7 +382,13 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                             v += tx[j].whi * ty[i].whi * __bfloat162float(s[(ty[i].hi * Ws + tx[j].hi) * sp]);
                             acc += p[i * K + j] * v;
                         }
-                    ob[NHWC ? (long long)c : (long long)c * hw] = __float2bfloat16_rn(acc * (1.0f / static_cast<float>(KK)));
+                    acc *= 1.0f / static_cast<float>(KK);
+                    if (prev != nullptr) {
+                        const float qm = __bfloat162float(mask[(long long)b * hw + qofs]);
+                        const __nv_bfloat16* pb = NHWC ? prev + ((long long)b * hw + qofs) * C + c0 : prev + ((long long)b * C + c0) * hw + qofs;
+                        acc = __bfloat162float(pb[NHWC ? (long long)c : (long long)c * hw]) * (1.f - qm) + acc * qm;
+                    }
+                    ob[NHWC ? (long long)c : (long long)c * hw] = __float2bfloat16_rn(acc);
                 }
             }
         }
@@ -368,8 +399,8 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
 }
 
 template <int K, int CN, bool NHWC>
-static int launch_tc(const void* src, const void* flow, const void* logits, void* out, void* probs, int B, int C, int Hs,
-                     int Ws, int H, int W, cudaStream_t st_) {
+static int launch_tc(const void* src, const void* flow, const void* logits, void* out, void* probs, const void* prev,
+                     const void* mask, int B, int C, int Hs, int Ws, int H, int W, cudaStream_t st_) {
     static const PFN_tmapEncodeTiled enc = tmap_encoder();
     if (enc == nullptr) return GFLA_E_NOTSUP;
     CUtensorMap tmap;
@@ -398,7 +429,9 @@ static int launch_tc(const void* src, const void* flow, const void* logits, void
     dim3 grid((unsigned)min(ngroups, sm_count()), (unsigned)(C / CN));
     kern<<<grid, NTHREADS, Smem<CN, SegW<NHWC>::value>::ALLOC, st_>>>(tmap, (const __nv_bfloat16*)src, (const float*)flow,
                                                    (const __nv_bfloat16*)logits, (__nv_bfloat16*)out,
-                                                   (__nv_bfloat16*)probs, B, C, Hs, Ws, H, W, tune_knob("GFLA_TC_PREFETCH", 0));
+                                                   (__nv_bfloat16*)probs, (const __nv_bfloat16*)prev,
+                                                   (const __nv_bfloat16*)mask, B, C, Hs, Ws, H, W,
+                                                   tune_knob("GFLA_TC_PREFETCH", 0));
     return launch_status();
 }
 
@@ -425,15 +458,16 @@ bool local_attn_fwd_tc_supported(int B, int C, int Hs, int Ws, int H, int W, int
     return layout == GFLA_NHWC ? aligned(out, 16) : (Ws % 8) == 0;
 }
 
-int local_attn_fwd_tc(const void* src, const void* flow, const void* logits, void* out, void* probs, int B, int C,
-                      int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, int layout, cudaStream_t st_) {
+int local_attn_fwd_tc(const void* src, const void* flow, const void* logits, void* out, void* probs, const void* prev,
+                      const void* mask, int B, int C, int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype,
+                      int layout, cudaStream_t st_) {
     if (!local_attn_fwd_tc_supported(B, C, Hs, Ws, H, W, k, dtype, flow_dtype, layout, src, out)) return GFLA_E_NOTSUP;
     const int cn = pick_cn(C);
     const bool nhwc = layout == GFLA_NHWC;
 #define GFLA_TC_CASE(K_, CN_)                                                                                        \
     if (k == K_ && cn == CN_)                                                                                        \
-        return nhwc ? tc::launch_tc<K_, CN_, true>(src, flow, logits, out, probs, B, C, Hs, Ws, H, W, st_)           \
-                    : tc::launch_tc<K_, CN_, false>(src, flow, logits, out, probs, B, C, Hs, Ws, H, W, st_);
+        return nhwc ? tc::launch_tc<K_, CN_, true>(src, flow, logits, out, probs, prev, mask, B, C, Hs, Ws, H, W, st_)  \
+                    : tc::launch_tc<K_, CN_, false>(src, flow, logits, out, probs, prev, mask, B, C, Hs, Ws, H, W, st_);
     GFLA_TC_CASE(5, 256) GFLA_TC_CASE(5, 128) GFLA_TC_CASE(5, 64)
     GFLA_TC_CASE(3, 256) GFLA_TC_CASE(3, 128) GFLA_TC_CASE(3, 64)
 #undef GFLA_TC_CASE

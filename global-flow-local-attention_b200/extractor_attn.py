@@ -95,10 +95,23 @@ class ExtractorAttn(nn.Module):
             x = layer(x)
         return x, block_source
 
-    def forward(self, source, target, flow_field):
+    def forward(self, source, target, flow_field, mask=None):
+        """Reference signature (source, target, flow_field).  Optional `mask` [B,1,H,W]: also apply the caller's
+        blend `target*(1-mask) + result*mask` (generator.py:130) -- fused into the kernel's store when no
+        gradient is needed (inference), composed with torch ops otherwise."""
         logits, block_source = self._logits(source, target, flow_field)
         if self.fused_softmax:
-            return local_attention(source, flow_field, logits, self.kernel_size)
+            if mask is None:
+                return local_attention(source, flow_field, logits, self.kernel_size)
+            needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (source, target, flow_field, logits, mask))
+            if needs_grad:
+                out_attn = local_attention(source, flow_field, logits, self.kernel_size)
+                return target * (1 - mask) + out_attn * mask
+            src = _keep_format(source)
+            fmt = torch.channels_last if (not src.is_contiguous()) else torch.contiguous_format
+            return F_.local_attn_blend_fwd(src, flow_field.contiguous(), logits.contiguous(),
+                                           target.contiguous(memory_format=fmt), mask.to(source.dtype), self.kernel_size)
+        assert mask is None, "mask blend is only fused for the softmax variant"
         # softmax=None in the reference means "apply the nonlinearity instead": keep the literal composition
         attn_param = self.reshape(self.fully_connect_layer[-1](logits), self.kernel_size)
         return torch.nn.functional.avg_pool2d(attn_param * block_source, self.kernel_size, self.kernel_size)

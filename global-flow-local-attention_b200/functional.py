@@ -170,6 +170,26 @@ def local_attn_fwd(source, flow, logits, k, return_probs=False, algo="auto"):
     return (out, probs) if return_probs else out
 
 
+def local_attn_blend_fwd(source, flow, logits, prev, mask, k, algo="auto"):
+    """out = prev * (1 - mask) + local_attention(source, flow, logits) * mask, in one kernel (forward only).
+    prev: [B,C,H,W] in the same memory format as source; mask: [B,1,H,W]."""
+    layout = _feature_layout(source)
+    assert _feature_layout(prev) == layout or prev.shape[1] == 1, "prev must use the same memory format as source"
+    assert flow.is_contiguous() and logits.is_contiguous()
+    mask = mask.contiguous()
+    _need_cuda(source, flow, logits, prev, mask)
+    bs, ds, hs, ws = source.size()
+    _, _, h, w = flow.size()
+    assert prev.shape == (bs, ds, h, w) and mask.shape == (bs, 1, h, w)
+    assert prev.dtype == source.dtype and mask.dtype == source.dtype and logits.dtype == source.dtype
+    out = _like_layout(source, (bs, ds, h, w), layout)
+    with torch.cuda.device_of(source):
+        _lib.check(_lib.lib().gfla_local_attn_blend_fwd(_p(source), _p(flow), _p(logits), _p(prev), _p(mask), _p(out), bs, ds,
+                                                        hs, ws, h, w, k, _dt(source), _dt(flow), layout, ALGO[algo],
+                                                        _stream(source)), "local_attn_blend_fwd")
+    return out
+
+
 def relayout(t: torch.Tensor, to_channels_last: bool) -> torch.Tensor:
     """Out-of-place NCHW <-> channels_last copy of a [B,C,H,W] tensor with the library's own transpose kernel."""
     _need_cuda(t)

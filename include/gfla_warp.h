@@ -154,6 +154,15 @@ int gfla_local_attn_fwd(const void* source, const void* flow, const void* logits
                         void* out, void* probs,
                         int B, int C, int Hs, int Ws, int H, int W, int k,
                         int dtype, int flow_dtype, int layout, int algo, gfla_stream_t stream);
+/* Same forward with the caller's mask blend fused into the store (generator.py:130,
+ * `out = out*(1-mask) + out_attn*mask`, and the two-branch sum at generator.py:496-498):
+ *     out = prev * (1 - mask) + local_attention(source, flow, logits) * mask
+ * prev [B,C,H,W] (same dtype/layout as out; may alias nothing), mask [B,1,H,W] planar, same dtype.
+ * Forward only (inference): training code keeps the unfused blend so autograd sees it. */
+int gfla_local_attn_blend_fwd(const void* source, const void* flow, const void* logits,
+                              const void* prev, const void* mask, void* out,
+                              int B, int C, int Hs, int Ws, int H, int W, int k,
+                              int dtype, int flow_dtype, int layout, int algo, gfla_stream_t stream);
 int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits,
                         const void* grad_out,
                         void* grad_source, void* grad_flow, void* grad_logits,

@@ -595,3 +595,46 @@ def test_relayout_roundtrip(F_, dt):
     assert y.is_contiguous(memory_format=torch.channels_last) and torch.equal(y, x)
     z = F_.relayout(y, False)
     assert z.is_contiguous() and torch.equal(z, x)
+
+
+# ----------------------------------------------------------------------------- fused mask blend (generator.py:130)
+@pytest.mark.parametrize("cfg", [("fp32", "nchw", "gather"), ("fp32", "nhwc", "gather"), ("bf16", "nchw", "tile"), ("bf16", "nhwc", "tile")])
+def test_local_attn_blend_fwd(F_, oracle_lib, cfg):
+    """out = prev*(1-mask) + local_attention*mask in one kernel == oracle attention blended on the host"""
+    prec, layout, algo = cfg
+    rng = np.random.default_rng(17)
+    B, C, H, W, k = 2, 64, 21, 40, 5
+    dt = torch.float32 if prec == "fp32" else torch.bfloat16
+    s = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32)).to(DEV).to(dt)
+    prev = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32)).to(DEV).to(dt)
+    mask = torch.from_numpy(rng.uniform(0, 1, (B, 1, H, W)).astype(np.float32)).to(DEV).to(dt)
+    f = torch.from_numpy(_flow(rng, "smooth", B, H, W).astype(np.float32)).to(DEV)
+    l = torch.from_numpy(rng.standard_normal((B, k * k, H, W)).astype(np.float32)).to(DEV).to(dt)
+    if layout == "nhwc":
+        s, prev = s.contiguous(memory_format=torch.channels_last), prev.contiguous(memory_format=torch.channels_last)
+    out = F_.local_attn_blend_fwd(s, f, l, prev, mask, k, algo=algo)
+    attn = oracle_lib.local_attn_fwd(host(s), f.cpu().numpy(), host(l), k)
+    ref = host(prev) * (1 - host(mask)) + attn * host(mask)
+    np.testing.assert_allclose(host(out), ref, rtol=0, atol=1e-5 if prec == "fp32" else 2e-2)   # bf16: |prev| ~ 3, one rounding
+
+
+def test_extractor_attn_mask_blend_module():
+    """ExtractorAttn(..., mask=m): fused store under no_grad == torch composition with autograd"""
+    import gfla_b200
+    torch.manual_seed(6)
+    C, k, B, H, W = 64, 3, 1, 16, 24
+    m = gfla_b200.ExtractorAttn(C, k, softmax=True).to(DEV).bfloat16().to(memory_format=torch.channels_last)
+    cl = torch.channels_last
+    src = torch.randn(B, C, H, W, device=DEV).bfloat16().contiguous(memory_format=cl)
+    tgt = torch.randn(B, C, H, W, device=DEV).bfloat16().contiguous(memory_format=cl)
+    flow = (torch.rand(B, 2, H, W, device=DEV) * 6 - 3)
+    mask = torch.rand(B, 1, H, W, device=DEV).bfloat16()
+    with torch.no_grad():
+        fused = m(src, tgt, flow, mask=mask)
+        plain = m(src, tgt, flow)
+    ref = tgt.float() * (1 - mask.float()) + plain.float() * mask.float()
+    assert (fused.float() - ref).abs().max().item() <= 3e-2
+    src.requires_grad_()
+    out = m(src, tgt, flow, mask=mask)        # gradient needed -> unfused composition, still correct and differentiable
+    out.float().sum().backward()
+    assert src.grad is not None and torch.isfinite(src.grad.float()).all()
