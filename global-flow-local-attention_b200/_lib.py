@@ -25,7 +25,8 @@ SIGNATURES = {
     "gfla_debug_set_buffer": [_vp],
     "gfla_relayout": [_vp, _vp] + [_i] * 6 + [_vp],
     "gfla_block_extract_fwd": [_vp, _vp, _vp] + [_i] * 9 + [_vp],
-    "gfla_block_extract_bwd": [_vp] * 5 + [_i] * 10 + [_vp],
+    "gfla_block_extract_bwd": [_vp] * 5 + [_i] * 11 + [_vp],
+    "gfla_convert": [_vp, _i, _vp, _i, ctypes.c_longlong, _vp],
     "gfla_attn_reshape_fwd": [_vp, _vp] + [_i] * 5 + [_vp],
     "gfla_attn_reshape_bwd": [_vp, _vp] + [_i] * 6 + [_vp],
     "gfla_resample2d_fwd": [_vp] * 3 + [_i] * 9 + [_vp],

@@ -4,7 +4,8 @@
 
 namespace gfla {
 int block_extract_fwd(const void*, const void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
-int block_extract_bwd(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int block_extract_bwd(const void*, const void*, const void*, void*, void*, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+int convert(const void*, int, void*, int, long long, cudaStream_t);
 int attn_reshape_fwd(const void*, void*, int, int, int, int, int, cudaStream_t);
 int attn_reshape_bwd(const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int resample2d_fwd(const void*, const void*, void*, int, int, int, int, int, int, int, int, int, cudaStream_t);
@@ -80,14 +81,24 @@ int gfla_block_extract_fwd(const void* source, const void* flow, void* out, int 
 
 int gfla_block_extract_bwd(const void* source, const void* flow, const void* grad_out, void* grad_source,
                            void* grad_flow, int B, int C, int Hs, int Ws, int Hf, int Wf, int k, int dtype,
-                           int flow_dtype, int accumulate, gfla_stream_t stream) {
+                           int flow_dtype, int grad_source_dtype, int accumulate, gfla_stream_t stream) {
     REQ_PTR(source); REQ_PTR(flow); REQ_PTR(grad_out); REQ_PTR(grad_source); REQ_PTR(grad_flow);
     if (!pos(B) || !pos(C) || !pos(Hs) || !pos(Ws) || !pos(Hf) || !pos(Wf) || k < 1 || k > 9) return GFLA_E_SHAPE;
     if (!dtype_known(dtype) || !flow_dtype_ok(dtype, flow_dtype)) return GFLA_E_DTYPE;
-    REQ_ALIGN(source, dtype); REQ_ALIGN(grad_out, dtype); REQ_ALIGN(grad_source, dtype);
+    // grad_source is stored in `dtype`, or in fp32 when `dtype` is a 16-bit type
+    if (grad_source_dtype != dtype && !((dtype == GFLA_BF16 || dtype == GFLA_F16) && grad_source_dtype == GFLA_F32)) return GFLA_E_DTYPE;
+    REQ_ALIGN(source, dtype); REQ_ALIGN(grad_out, dtype); REQ_ALIGN(grad_source, grad_source_dtype);
     REQ_ALIGN(flow, flow_dtype); REQ_ALIGN(grad_flow, flow_dtype);
     return block_extract_bwd(source, flow, grad_out, grad_source, grad_flow, B, C, Hs, Ws, Hf, Wf, k, dtype, flow_dtype,
-                             accumulate, (cudaStream_t)stream);
+                             grad_source_dtype, accumulate, (cudaStream_t)stream);
+}
+
+int gfla_convert(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, gfla_stream_t stream) {
+    REQ_PTR(src); REQ_PTR(dst);
+    if (n <= 0) return GFLA_E_SHAPE;
+    if (!dtype_known(src_dtype) || !dtype_known(dst_dtype)) return GFLA_E_DTYPE;
+    REQ_ALIGN(src, src_dtype); REQ_ALIGN(dst, dst_dtype);
+    return convert(src, src_dtype, dst, dst_dtype, n, (cudaStream_t)stream);
 }
 
 int gfla_attn_reshape_fwd(const void* in, void* out, int B, int H, int W, int k, int dtype, gfla_stream_t stream) {

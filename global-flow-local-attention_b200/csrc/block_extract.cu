@@ -54,10 +54,12 @@ k_block_extract_fwd(const T* __restrict__ src, const TF* __restrict__ flow, T* _
     }
 }
 
-template <typename T, typename TF>
+// TG = storage type of grad_source: T, or float for 16-bit T (native fp32 red.global instead of the
+// compare-and-swap loop a 16-bit scalar atomicAdd turns into; the caller narrows the buffer afterwards)
+template <typename T, typename TF, typename TG>
 __global__ void __launch_bounds__(128)
 k_block_extract_bwd(const T* __restrict__ src, const TF* __restrict__ flow, const T* __restrict__ gout,
-                    T* __restrict__ gsrc, TF* __restrict__ gflow,
+                    TG* __restrict__ gsrc, TF* __restrict__ gflow,
                     int B, int C, int Hs, int Ws, int Hf, int Wf, int k, int c_per_slice, int slices) {
     using A = typename Acc<T>::type;
     const long long total = (long long)B * Hf * Wf;
@@ -78,7 +80,7 @@ k_block_extract_bwd(const T* __restrict__ src, const TF* __restrict__ flow, cons
             const AxisTap<A> tx = axis_tap<A>(flow_x, j - k / 2, xf, Ws);
             const int oLT = ty.lo * Ws + tx.lo, oRT = ty.lo * Ws + tx.hi, oLB = ty.hi * Ws + tx.lo, oRB = ty.hi * Ws + tx.hi;
             const T* s = src + ((long long)b * C + c0) * spl;
-            T* gs = gsrc + ((long long)b * C + c0) * spl;
+            TG* gs = gsrc + ((long long)b * C + c0) * spl;
             const T* go = gout + ((long long)b * C + c0) * opl + (long long)(yf * k + i) * Wo + (xf * k + j);
             for (int c = c0; c < c1; ++c, s += spl, gs += spl, go += opl) {
                 const A g = ld(go);
@@ -130,6 +132,14 @@ k_attn_reshape_bwd(const T* __restrict__ gout, T* __restrict__ gin, int B, int H
     st(gin + pos, accumulate ? static_cast<A>(ld(gin + pos)) + g : g);
 }
 
+// element-wise dtype conversion (narrowing an fp32 gradient accumulator to 16-bit storage, etc.)
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256)
+k_convert(const TS* __restrict__ src, TD* __restrict__ dst, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st(dst + i, ld(src + i));
+}
+
 // ---------------------------------------------------------------------------
 // host launchers (called from api.cu)
 // ---------------------------------------------------------------------------
@@ -145,7 +155,7 @@ static int launch_be_fwd(const void* src, const void* flow, void* out, int B, in
     return launch_status();
 }
 
-template <typename T, typename TF>
+template <typename T, typename TF, typename TG>
 static int launch_be_bwd(const void* src, const void* flow, const void* gout, void* gsrc, void* gflow, int B, int C,
                          int Hs, int Ws, int Hf, int Wf, int k, cudaStream_t st_) {
     const long long total = (long long)B * Hf * Wf;
@@ -154,7 +164,7 @@ static int launch_be_bwd(const void* src, const void* flow, const void* gout, vo
     const int cps = (C + slices0 - 1) / slices0;
     const int slices = (C + cps - 1) / cps;
     dim3 grid((unsigned)((total + threads - 1) / threads), (unsigned)slices);
-    k_block_extract_bwd<T, TF><<<grid, threads, 0, st_>>>((const T*)src, (const TF*)flow, (const T*)gout, (T*)gsrc,
+    k_block_extract_bwd<T, TF, TG><<<grid, threads, 0, st_>>>((const T*)src, (const TF*)flow, (const T*)gout, (TG*)gsrc,
                                                          (TF*)gflow, B, C, Hs, Ws, Hf, Wf, k, cps, slices);
     return launch_status();
 }
@@ -168,16 +178,30 @@ int block_extract_fwd(const void* src, const void* flow, void* out, int B, int C
 }
 
 int block_extract_bwd(const void* src, const void* flow, const void* gout, void* gsrc, void* gflow, int B, int C,
-                      int Hs, int Ws, int Hf, int Wf, int k, int dtype, int flow_dtype, int accumulate,
+                      int Hs, int Ws, int Hf, int Wf, int k, int dtype, int flow_dtype, int gs_dtype, int accumulate,
                       cudaStream_t st_) {
     if (!accumulate) {
-        cudaMemsetAsync(gsrc, 0, (size_t)B * C * Hs * Ws * elem_size(dtype), st_);
+        cudaMemsetAsync(gsrc, 0, (size_t)B * C * Hs * Ws * elem_size(gs_dtype), st_);
         cudaMemsetAsync(gflow, 0, (size_t)B * 2 * Hf * Wf * elem_size(flow_dtype), st_);
     }
     return GFLA_DISPATCH_T(dtype, [&]() -> int {
-        if (flow_dtype == dtype) return launch_be_bwd<T, T>(src, flow, gout, gsrc, gflow, B, C, Hs, Ws, Hf, Wf, k, st_);
-        return launch_be_bwd<T, float>(src, flow, gout, gsrc, gflow, B, C, Hs, Ws, Hf, Wf, k, st_);
+        if (gs_dtype != dtype) {   // 16-bit data, fp32 grad_source buffer
+            if (flow_dtype == dtype) return launch_be_bwd<T, T, float>(src, flow, gout, gsrc, gflow, B, C, Hs, Ws, Hf, Wf, k, st_);
+            return launch_be_bwd<T, float, float>(src, flow, gout, gsrc, gflow, B, C, Hs, Ws, Hf, Wf, k, st_);
+        }
+        if (flow_dtype == dtype) return launch_be_bwd<T, T, T>(src, flow, gout, gsrc, gflow, B, C, Hs, Ws, Hf, Wf, k, st_);
+        return launch_be_bwd<T, float, T>(src, flow, gout, gsrc, gflow, B, C, Hs, Ws, Hf, Wf, k, st_);
     });
+}
+
+int convert(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, cudaStream_t st_) {
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+#define GFLA_CVT(SD, ST, DD, DT) \
+    if (src_dtype == SD && dst_dtype == DD) { k_convert<ST, DT><<<blocks, 256, 0, st_>>>((const ST*)src, (DT*)dst, n); return launch_status(); }
+    GFLA_CVT(GFLA_F32, float, GFLA_BF16, __nv_bfloat16) GFLA_CVT(GFLA_F32, float, GFLA_F16, __half)
+    GFLA_CVT(GFLA_BF16, __nv_bfloat16, GFLA_F32, float) GFLA_CVT(GFLA_F16, __half, GFLA_F32, float)
+#undef GFLA_CVT
+    return GFLA_E_DTYPE;
 }
 
 int attn_reshape_fwd(const void* in, void* out, int B, int H, int W, int k, int dtype, cudaStream_t st_) {

@@ -57,6 +57,15 @@ def block_extract_fwd(source: torch.Tensor, flow: torch.Tensor, k: int) -> torch
     return out
 
 
+def convert(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """fp32 <-> bf16/f16 copy with the library's kernel (contiguous tensors)."""
+    assert t.is_contiguous()
+    out = torch.empty_like(t, dtype=dtype)
+    with torch.cuda.device_of(t):
+        _lib.check(_lib.lib().gfla_convert(_p(t), _dt(t), _p(out), _DT[dtype], t.numel(), _stream(t)), "convert")
+    return out
+
+
 def block_extract_bwd(source, flow, grad_out, k, grad_source=None, grad_flow=None):
     """Returns (grad_source, grad_flow).  If buffers are passed, gradients are ADDED
     into them (reference contract, block_extractor.py:35-40)."""
@@ -65,13 +74,20 @@ def block_extract_bwd(source, flow, grad_out, k, grad_source=None, grad_flow=Non
     _need_cuda(source, flow, grad_out)
     bs, ds, hs, ws = source.size()
     _, _, hf, wf = flow.size()
-    accumulate = 1
+    accumulate, narrow = 1, False
     if grad_source is None:
-        grad_source, grad_flow, accumulate = torch.empty_like(source), torch.empty_like(flow), 0
+        accumulate = 0
+        # 16-bit storage: scatter into an fp32 buffer (native red.global.f32; a 16-bit scalar atomicAdd is a
+        # compare-and-swap loop, ~50x slower) and narrow afterwards
+        narrow = source.dtype in (torch.bfloat16, torch.float16)
+        grad_source = torch.empty(source.shape, dtype=torch.float32 if narrow else source.dtype, device=source.device)
+        grad_flow = torch.empty_like(flow)
     with torch.cuda.device_of(source):
         _lib.check(_lib.lib().gfla_block_extract_bwd(_p(source), _p(flow), _p(grad_out), _p(grad_source), _p(grad_flow),
-                                                     bs, ds, hs, ws, hf, wf, k, _dt(source), _dt(flow), accumulate,
-                                                     _stream(source)), "block_extract_bwd")
+                                                     bs, ds, hs, ws, hf, wf, k, _dt(source), _dt(flow), _dt(grad_source),
+                                                     accumulate, _stream(source)), "block_extract_bwd")
+    if narrow:
+        grad_source = convert(grad_source, source.dtype)
     return grad_source, grad_flow
 
 

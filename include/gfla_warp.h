@@ -96,10 +96,15 @@ int gfla_relayout(const void* src, void* dst, int B, int C, int H, int W, int dt
 int gfla_block_extract_fwd(const void* source, const void* flow, void* out,
                            int B, int C, int Hs, int Ws, int Hf, int Wf, int k,
                            int dtype, int flow_dtype, gfla_stream_t stream);
+/* grad_source_dtype: == dtype (reference contract), or GFLA_F32 when dtype is a 16-bit type: the scatter then
+ * uses native fp32 red.global instead of 16-bit compare-and-swap atomics; narrow with gfla_convert(). */
 int gfla_block_extract_bwd(const void* source, const void* flow, const void* grad_out,
                            void* grad_source, void* grad_flow,
                            int B, int C, int Hs, int Ws, int Hf, int Wf, int k,
-                           int dtype, int flow_dtype, int accumulate, gfla_stream_t stream);
+                           int dtype, int flow_dtype, int grad_source_dtype, int accumulate,
+                           gfla_stream_t stream);
+/* element-wise dtype conversion between fp32 and bf16 / f16 (n elements, contiguous) */
+int gfla_convert(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, gfla_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
  * local_attn_reshape  ([B,k*k,H,W] -> [B,1,k*H,k*W], depth-to-space)

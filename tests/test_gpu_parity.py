@@ -638,3 +638,17 @@ def test_extractor_attn_mask_blend_module():
     out = m(src, tgt, flow, mask=mask)        # gradient needed -> unfused composition, still correct and differentiable
     out.float().sum().backward()
     assert src.grad is not None and torch.isfinite(src.grad.float()).all()
+
+
+def test_block_extractor_bf16_backward_fp32_accumulation(F_, oracle_lib):
+    """16-bit storage: grad_source is scattered into an fp32 buffer and narrowed once (functional.block_extract_bwd)"""
+    rng = np.random.default_rng(23)
+    B, C, H, W, k = 1, 6, 12, 14, 3
+    s = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32)).to(DEV).bfloat16()
+    f = torch.from_numpy(rng.uniform(-4, 4, (B, 2, H, W)).astype(np.float32)).to(DEV)
+    g = torch.from_numpy(rng.standard_normal((B, C, k * H, k * W)).astype(np.float32)).to(DEV).bfloat16()
+    gs, gf = F_.block_extract_bwd(s, f, g, k)
+    assert gs.dtype == torch.bfloat16
+    ogs, ogf = oracle_lib.block_extract_bwd(host(s), f.cpu().numpy(), host(g), k)
+    np.testing.assert_allclose(host(gs), ogs, rtol=1e-2, atol=1e-2 * max(1.0, float(np.abs(ogs).max())))
+    np.testing.assert_allclose(host(gf), ogf, rtol=1e-3, atol=1e-3 * max(1.0, float(np.abs(ogf).max())))

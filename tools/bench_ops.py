@@ -25,7 +25,7 @@ def smooth(B, H, W):
     c = (torch.rand(B, 2, H // 16, W // 16, device=dev) * 16 - 8)
     return torch.nn.functional.interpolate(c, size=(H, W), mode="bilinear", align_corners=True).contiguous()
 
-which = sys.argv[1:] or ["cfg3", "cfg2_unfused", "cfg2_fp32"]
+which = sys.argv[1:] or ["cfg3", "cfg2_unfused", "cfg2_fp32", "module"]
 torch.manual_seed(0)
 if "cfg3" in which:   # resample2d fwd+bwd, B=32 C=128 512x512 fp32 (BASELINE.json configs[2]); ks=2 sigma=5 and ks=4 sigma=2
     B, C, H, W = 32, 128, 512, 512
@@ -56,3 +56,32 @@ if "cfg2_fp32" in which:   # fused op in fp32 (CUDA-core gather kernels), B=4
     emit("local_attn_fwd fp32 (gather kernel)", t, px, px * (2 * C * 4 + 8 + k * k * 4), config="B=4 C=256 256x256 k=5")
     t = timed(lambda: F_.local_attn_bwd(s, fl, l, g, k), n=2, w=1)
     emit("local_attn_bwd fp32 (gather kernel, scalar atomics)", t, px, px * (3 * C * 4 + 16 + 2 * k * k * 4), config="B=4 C=256 256x256 k=5")
+
+if "module" in which:   # ExtractorAttn at the shapes the pose generator uses: fused module vs the literal op chain
+    import gfla_b200
+    for (C, HW, k) in ((256, 32, 3), (128, 64, 5)):
+        B = 8
+        cl = torch.channels_last
+        m = gfla_b200.ExtractorAttn(C, k, softmax=True).to(dev).bfloat16().to(memory_format=cl)
+        src = torch.randn(B, C, HW, HW, device=dev).bfloat16().contiguous(memory_format=cl).requires_grad_()
+        tgt = torch.randn(B, C, HW, HW, device=dev).bfloat16().contiguous(memory_format=cl).requires_grad_()
+        flow = (torch.rand(B, 2, HW, HW, device=dev) * 8 - 4).requires_grad_()
+        ex, rs = gfla_b200.BlockExtractor(k), gfla_b200.LocalAttnReshape()
+
+        def ours(train):
+            out = m(src, tgt, flow)
+            if train: out.float().sum().backward()
+
+        def literal(train):   # base_function.py:804-810 verbatim, on our unfused kernels
+            bs = ex(src, flow); bt = ex(tgt, torch.zeros_like(flow))
+            attn = m.fully_connect_layer(torch.cat((bt, bs), 1))
+            out = torch.nn.functional.avg_pool2d(rs(attn, k) * bs, k, k)
+            if train: out.float().sum().backward()
+
+        px = B * HW * HW
+        for name, fn in (("ExtractorAttn (fused tail, this library)", ours), ("literal reference op chain on our unfused kernels", literal)):
+            with torch.no_grad():
+                f = timed(lambda: fn(False))
+            fb = timed(lambda: fn(True), n=3, w=2)
+            print(json.dumps({"op": name, "config": f"B={B} C={C} {HW}x{HW} k={k} bf16 channels_last", "fwd_ms": round(f, 4),
+                              "fwd_bwd_ms": round(fb, 4), "Mpixels_per_s_fwd_bwd": round(px / fb / 1e3, 2)}), flush=True)
