@@ -73,13 +73,16 @@ struct Smem {
 // to fetch 32-byte runs, one per channel, and needs its box origin aligned to 8 pixels), the box origin is
 // unconstrained in x, the smem tile is an MN-major (channel-contiguous) UMMA B operand, and the epilogue
 // stores 64 contiguous bytes per thread.
+// `knobs` (environment GFLA_TC_KNOBS, default 0 = production): bits 0-7 = 1/2 L2 prefetch of the next group's source box
+// (tensor / bulk; measured: no gain), bit 8 = skip output stores, bit 9 = skip window construction, bit 10 = skip the
+// slab scatter -- timing experiments only, results are wrong when bits 8-10 are set.
 template <int K, int CN, bool NHWC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfloat16* __restrict__ src,
                     const float* __restrict__ flow, const __nv_bfloat16* __restrict__ logits,
                     __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ probs,
                     const __nv_bfloat16* __restrict__ prev, const __nv_bfloat16* __restrict__ mask, int B, int C, int Hs,
-                    int Ws, int H, int W, int prefetch_mode) {
+                    int Ws, int H, int W, int knobs) {
     constexpr int FBW = SegW<NHWC>::value;
     using SM = Smem<CN, FBW>;
     constexpr int K1 = K + 1, KK = K * K;
@@ -94,7 +97,6 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
     uint64_t* info_full = bars + 3 * NSTAGE + 4;  // [NINFO]
     GroupInfo* infos = reinterpret_cast<GroupInfo*>(smem + SM::OFF_INFO);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_TMEM);
-    __nv_bfloat16* wsm = reinterpret_cast<__nv_bfloat16*>(smem + SM::OFF_W);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gxn = (W + GW - 1) / GW, gyn = (H + GH - 1) / GH;
@@ -133,12 +135,12 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             if (gn < ngroups) {
                 bbox_of(gn, nx0, ny0, nx1, ny1);
                 const int bn = gn / (gxn * gyn), prow = ny1 - ny0 + 1;
-                if ((prefetch_mode & 255) == 2 && NHWC && CN == C) {
+                if ((knobs & 255) == 2 && NHWC && CN == C) {
                     // channels-last, all channels in this CTA: a row segment of the box is one contiguous range
                     const uint32_t bytes = static_cast<uint32_t>(nx1 - nx0 + 1) * C * 2;
                     for (int r = lane; r < prow; r += 32)
                         prefetch_l2_bulk(src + (((long long)bn * Hs + ny0 + r) * Ws + nx0) * C, bytes);
-                } else if ((prefetch_mode & 255) == 1) {
+                } else if ((knobs & 255) == 1) {
                     const int pcb = (nx1 - nx0 + FBW) / FBW;
                     for (int idx = lane; idx < pcb * prow; idx += 32) {
                         const int cb = idx / prow, yy = ny0 + idx % prow;
@@ -234,7 +236,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             const bool valid = px < W && py < H;
             int X0 = 0, Y0 = 0;
             bool live = false;
-            if (valid && !(prefetch_mode & 512)) {   // bit 9: timing experiment, skip the per-pixel window construction
+            if (valid && !(knobs & 512)) {   // bit 9: timing experiment, skip the per-pixel window construction
                 const long long pofs = (long long)py * W + px;
                 float p[KK];
                 pixel_softmax_f32<KK>(logits + (long long)b * KK * hw + pofs, hw, p);
@@ -256,7 +258,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             const GroupInfo inf = infos[gi % NINFO];
             for (int cb = 0; cb < inf.ncb; ++cb) {
                 const int e0 = X0 - (inf.x0 + cb * FBW);           // box position of window column 0
-                const bool cols_hit = live && e0 > -K1 && e0 < FBW && !(prefetch_mode & 1024);   // bit 10: timing experiment
+                const bool cols_hit = live && e0 > -K1 && e0 < FBW && !(knobs & 1024);   // bit 10: timing experiment
                 for (int rc = 0; rc < inf.nrc; ++rc, ++it) {
                     const int slot = it % NSTAGE;
                     mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x020200 | slot, it);
@@ -303,7 +305,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                 uint32_t v[32];
                 tmem_ld_32x32(taddr + cc * 32, v);
                 tmem_ld_wait();
-                if (valid && regular && !(prefetch_mode & 256)) {   // bit 8: debug knob, skip the stores
+                if (valid && regular && !(knobs & 256)) {   // bit 8: debug knob, skip the stores
                     if (pv != nullptr) {   // blend in fp32 before the single rounding to bf16
                         if (NHWC) {
                             const uint4* p4 = reinterpret_cast<const uint4*>(pv + cc * 32);
@@ -431,7 +433,7 @@ static int launch_tc(const void* src, const void* flow, const void* logits, void
                                                    (const __nv_bfloat16*)logits, (__nv_bfloat16*)out,
                                                    (__nv_bfloat16*)probs, (const __nv_bfloat16*)prev,
                                                    (const __nv_bfloat16*)mask, B, C, Hs, Ws, H, W,
-                                                   tune_knob("GFLA_TC_PREFETCH", 0));
+                                                   tune_knob("GFLA_TC_KNOBS", 0));
     return launch_status();
 }
 
