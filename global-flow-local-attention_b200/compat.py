@@ -69,7 +69,12 @@ def _rs_backward(input1, input2, grad_output, grad_input1, grad_input2, kernel_s
     return 1
 
 
-def install(python_wrappers: bool = True) -> None:
+def install(python_wrappers: bool = True, reference_root: str | None = None, fuse_extractor_attn: bool = True) -> None:
+    """Register the legacy names.  With `reference_root` (a checkout of the reference), the stubbed
+    `model.networks` package also resolves the reference's own network files (base_function.py, generator.py,
+    ...), so `from model.networks.generator import PoseGenerator` works without importing the reference's
+    `model/__init__.py` (which drags in datasets / visualisation dependencies); and, if `fuse_extractor_attn`,
+    the reference's `ExtractorAttn` class is replaced by the fused drop-in (same parameters / state_dict)."""
     sys.modules["block_extractor_cuda"] = _mk("block_extractor_cuda", forward=_be_forward, backward=_be_backward)
     sys.modules["local_attn_reshape_cuda"] = _mk("local_attn_reshape_cuda", forward=_lr_forward, backward=_lr_backward)
     sys.modules["resample2d_cuda"] = _mk("resample2d_cuda", forward=_rs_forward, backward=_rs_backward)
@@ -85,3 +90,14 @@ def install(python_wrappers: bool = True) -> None:
     sys.modules["model.networks.block_extractor.block_extractor"] = block_extractor
     sys.modules["model.networks.local_attn_reshape.local_attn_reshape"] = local_attn_reshape
     sys.modules["model.networks.resample2d_package.resample2d"] = resample2d
+    if reference_root is not None:
+        import importlib
+        import os
+        nets = os.path.join(reference_root, "model", "networks")
+        if not os.path.isdir(nets):
+            raise FileNotFoundError(nets)
+        sys.modules["model.networks"].__path__ = [nets]
+        if fuse_extractor_attn:
+            from .extractor_attn import ExtractorAttn
+            base_function = importlib.import_module("model.networks.base_function")
+            base_function.ExtractorAttn = ExtractorAttn      # generator.py does `from ...base_function import *`
