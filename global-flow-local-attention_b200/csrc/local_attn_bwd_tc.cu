@@ -8,8 +8,8 @@
 // our CUDA-core kernel -- issue one atomicAdd per (pixel, channel, tap corner): 4*k*k*C*H*W*B = 2.7e10
 // scalar atomics at cfg2.  Here the scatter is a GEMM per pixel group:
 //
-//   * K = the 128 pixels of a 16x8 group;  A = Wfull^T, i.e. the [128 pixels][16 positions] weight slabs of
-//     the forward kernel read as an MN-major operand (M = source positions: 8 row segments of 16 = 128);
+//   * K = the 128 pixels of a 16x8 group;  A = Wfull^T, i.e. the [128 pixels][32 positions] weight slabs of
+//     the forward kernel read as an MN-major operand (M = source positions: 4 row segments of 32 = 128);
 //   * B = the grad_out tile [128 pixels][CN channels], one TMA box per 64 channels (128-byte rows,
 //     MN-major = channel-contiguous);
 //   * D[128 positions][CN channels] accumulates in TMEM (fp32), double-buffered;
@@ -32,7 +32,10 @@
 namespace gfla {
 namespace tc {
 
-constexpr int GS_ROWS = 8;        // source rows per block: M = 8 segments x 16 positions = 128
+constexpr int GS_ROWS = 4;        // source rows per block: M = 4 segments x 32 positions = 128 (blocks of 32 x 4 waste
+                                  // far less of the footprint than 16 x 8 ones: rows are needed in multiples of 4, not 8)
+constexpr int GS_BW = 32;         // positions per row segment
+constexpr int GS_SLAB = 128 * GS_BW * 2;   // [128 pixels][32 positions] bf16, 64-byte rows, 64B swizzle
 constexpr int GS_NA = 2;          // weight-slab stages
 constexpr int GS_NINFO = 8;
 constexpr int GS_NTHREADS = 320;
@@ -41,7 +44,7 @@ template <int CN>
 struct SmemGS {
     static constexpr int G_CG = 128 * 128;                     // [128 pixels][64 channels] bf16
     static constexpr int G_BYTES = (CN / 64) * G_CG;
-    static constexpr int A_STAGE = GS_ROWS * A_SLAB;           // 8 slabs of [128 pixels][16 positions]
+    static constexpr int A_STAGE = GS_ROWS * GS_SLAB;          // 4 slabs of [128 pixels][32 positions]
     static constexpr int O_BUF = 128 * 128;                    // staging: [128 positions][64 channels] bf16
     static constexpr int OFF_G = 0;
     static constexpr int OFF_A = OFF_G + G_BYTES;
@@ -121,7 +124,7 @@ k_local_attn_bwd_gs_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             int x0, y0, x1, y1;
             group_bbox<K>(flow, b, gx0, gy0, H, W, Hs, Ws, lane, false, x0, y0, x1, y1);
             if (lane == 0) {
-                infos[gi % GS_NINFO] = GroupInfo{x0, y0, (x1 - x0 + BW) / BW, (y1 - y0 + GS_ROWS) / GS_ROWS};
+                infos[gi % GS_NINFO] = GroupInfo{x0, y0, (x1 - x0 + GS_BW) / GS_BW, (y1 - y0 + GS_ROWS) / GS_ROWS};
                 mbar_arrive(&info_full[gi % GS_NINFO]);
             }
             mbar_wait(g_empty, (gi & 1) ^ 1, 0x000600, gi);
@@ -154,8 +157,8 @@ k_local_attn_bwd_gs_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                     const uint32_t d_tmem = tmem_base + buf * CN;
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {  // 16 pixels per MMA
-                        // A^T: M = positions (16 per slab, LBO = next slab), K = pixels (8 per 256-byte atom)
-                        const uint64_t ad = make_smem_desc(a0 + ks * 512, A_SLAB, 256, kSwizzle32);
+                        // A^T: M = positions (32 per slab, LBO = next slab), K = pixels (8 per 512-byte atom)
+                        const uint64_t ad = make_smem_desc(a0 + ks * 1024, GS_SLAB, 512, kSwizzle64);
                         // B: N = channels (64 per 128-byte row, LBO = next channel group), K = pixels (8 per 1 KB atom)
                         const uint64_t bd = make_smem_desc(b0 + ks * 2048, SM::G_CG, 1024, kSwizzle128);
                         umma_f16(d_tmem, ad, bd, idesc, ks != 0 ? 1u : 0u);
@@ -172,8 +175,8 @@ k_local_attn_bwd_gs_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         const int q = warp & 3, m = q * 32 + lane;
         const float inv_kk = 1.0f / static_cast<float>(KK);
         const uint32_t wsm_a = smem_u32(smem + SM::OFF_W) + m * 4;
-        const uint32_t a_base = smem_u32(smem + SM::OFF_A) + m * 32;
-        const uint32_t swz = ((m >> 2) & 1) << 4;
+        const uint32_t a_base = smem_u32(smem + SM::OFF_A) + m * (GS_BW * 2);
+        const uint32_t swz = ((m >> 1) & 3) << 4;   // 64B swizzle: 16B chunk ^= bits 1-2 of the row
         uint32_t blk = 0, dirty = 0xffffffffu;
         int gi = 0;
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
@@ -198,8 +201,8 @@ k_local_attn_bwd_gs_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             mbar_wait(&info_full[gi % GS_NINFO], (gi / GS_NINFO) & 1, 0x020500, gi);
             const GroupInfo inf = infos[gi % GS_NINFO];
             for (int cb = 0; cb < inf.ncb; ++cb) {
-                const int e0 = X0 - (inf.x0 + cb * BW);
-                const bool cols_hit = live && e0 > -K1 && e0 < BW;
+                const int e0 = X0 - (inf.x0 + cb * GS_BW);
+                const bool cols_hit = live && e0 > -K1 && e0 < GS_BW;
                 for (int rb = 0; rb < inf.nrc; ++rb, ++blk) {
                     const int st = blk % GS_NA;
                     mbar_wait(&a_empty[st], ((blk / GS_NA) & 1) ^ 1, 0x020200 | st, blk);
@@ -208,7 +211,7 @@ k_local_attn_bwd_gs_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                     bool wrote = false;
 #pragma unroll
                     for (int seg = 0; seg < GS_ROWS; ++seg)
-                        wrote |= fill_slab_row<K>(a_stage + seg * A_SLAB, swz, wsm_a, cols_hit, (R0 + seg) - Y0, e0, dirty,
+                        wrote |= fill_slab_row<K, GS_BW>(a_stage + seg * GS_SLAB, swz, wsm_a, cols_hit, (R0 + seg) - Y0, e0, dirty,
                                                   1u << (st * GS_ROWS + seg));
                     if (wrote) fence_proxy_async_smem();
                     mbar_arrive(&a_full[st]);
@@ -217,7 +220,8 @@ k_local_attn_bwd_gs_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         }
     } else {
         // ================================================================= epilogue
-        const int q = warp & 3, t = q * 32 + lane;          // source position of the block: row t/16, column t%16
+        const int q = warp & 3, t = q * 32 + lane;          // source position of the block: row t/32, column t%32
+                                                            // (as a PIXEL index for the irregular-tap pass below: 16 wide)
         const uint32_t o_base = smem_u32(smem + SM::OFF_O);
         const bool issuer = (warp == 6 && lane == 0);
         uint32_t blk = 0, oi = 0;   // oi: running index of the staging tile (alternates between the two buffers)
@@ -306,7 +310,7 @@ k_local_attn_bwd_gs_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                         fence_proxy_async_smem();
                         named_bar_sync(2, 128);           // tile complete
                         if (issuer) {
-                            tma_reduce_add_4d(&tmap_gs, o_base + (oi & 1) * SM::O_BUF, c0 + cg * 64, inf.x0 + cb * BW,
+                            tma_reduce_add_4d(&tmap_gs, o_base + (oi & 1) * SM::O_BUF, c0 + cg * 64, inf.x0 + cb * GS_BW,
                                               inf.y0 + rb * GS_ROWS, b);
                             bulk_commit();
                             bulk_wait_read<1>();          // the OTHER buffer's reduce has finished reading smem
@@ -328,7 +332,8 @@ static int launch_gs(const void* flow, const void* logits, const void* gout, voi
     if (enc == nullptr) return GFLA_E_NOTSUP;
     CUtensorMap tg, tgs;
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const cuuint32_t box[4] = {64, GW, GH, 1};
+    const cuuint32_t box[4] = {64, GW, GH, 1};             // grad_out tile: 16 x 8 pixels
+    const cuuint32_t rbox[4] = {64, GS_BW, GS_ROWS, 1};    // reduce-add tile: 32 x 4 source positions
     {
         const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         const cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
@@ -340,7 +345,7 @@ static int launch_gs(const void* flow, const void* logits, const void* gout, voi
     {
         const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)B};
         const cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)Ws * C * 2, (cuuint64_t)Hs * Ws * C * 2};
-        if (enc(&tgs, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, gsrc, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        if (enc(&tgs, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, gsrc, gdim, gstr, rbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) !=
             CUDA_SUCCESS)
             return GFLA_E_NOTSUP;
