@@ -11,7 +11,7 @@
 //
 //   D[128 pixels][64 positions] = G[128 pixels][C] * S[64 positions][C]^T
 //
-// per pipeline stage (4 source rows x 16 columns of the group's tap footprint): both operands are K-major
+// per pipeline stage (2 source rows x 32 columns of the group's tap footprint): both operands are K-major
 // (channel-contiguous) TMA boxes -- grad_out tile [128 px][64 ch] per channel group, source rows
 // [64 positions][64 ch] per channel group -- so there is no operand construction at all.  Each epilogue
 // thread (one per pixel) then picks its window entries out of the 64 accumulator columns and, after the
@@ -23,7 +23,8 @@
 namespace gfla {
 namespace tc {
 
-constexpr int Q_ROWS = 4;          // source rows per stage: N = 4 x 16 = 64 positions
+constexpr int Q_ROWS = 2;          // source rows per stage: N = 2 x 32 = 64 positions (rows rounded to 2, one 32-wide
+constexpr int Q_BW = 32;           // segment usually spans the whole footprint of a 16-pixel-wide group)
 constexpr int Q_NS = 4;            // source-row stages (64 KB grad_out tile + 4 x 32 KB)
 constexpr int Q_NACC = 4;          // accumulator buffers of 64 TMEM columns
 constexpr int Q_NINFO = 8;
@@ -33,7 +34,7 @@ template <int CN>
 struct SmemQ {
     static constexpr int G_CG = 128 * 128;                 // [128 pixels][64 channels]
     static constexpr int G_BYTES = (CN / 64) * G_CG;
-    static constexpr int S_CG = Q_ROWS * BW * 128;         // [64 positions][64 channels] = 8 KB
+    static constexpr int S_CG = Q_ROWS * Q_BW * 128;       // [64 positions][64 channels] = 8 KB
     static constexpr int S_STAGE = (CN / 64) * S_CG;
     static constexpr int OFF_G = 0;
     static constexpr int OFF_S = OFF_G + G_BYTES;
@@ -95,7 +96,7 @@ k_local_attn_bwd_q_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
             const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
             int x0, y0, x1, y1;
             group_bbox<K>(flow, b, gx0, gy0, H, W, Hs, Ws, lane, false, x0, y0, x1, y1);
-            const int ncb = (x1 - x0 + BW) / BW, nrc = (y1 - y0 + Q_ROWS) / Q_ROWS;
+            const int ncb = (x1 - x0 + Q_BW) / Q_BW, nrc = (y1 - y0 + Q_ROWS) / Q_ROWS;
             if (lane == 0) {
                 infos[gi % Q_NINFO] = GroupInfo{x0, y0, ncb, nrc};
                 mbar_arrive(&info_full[gi % Q_NINFO]);
@@ -117,14 +118,14 @@ k_local_attn_bwd_q_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
 #pragma unroll
                         for (int cg = 0; cg < CN / 64; ++cg)
                             tma_load_4d(smem + SM::OFF_S + slot * SM::S_STAGE + cg * SM::S_CG, &tmap_s, &s_full[slot], cg * 64,
-                                        x0 + cb * BW, y0 + rc * Q_ROWS, b);
+                                        x0 + cb * Q_BW, y0 + rc * Q_ROWS, b);
                     }
                     __syncwarp();
                 }
         }
     } else if (warp == 1) {
         // ================================================================= MMA issuer
-        constexpr uint32_t idesc = make_idesc_f16(128, Q_ROWS * BW, true, false, false);  // both K-major
+        constexpr uint32_t idesc = make_idesc_f16(128, Q_ROWS * Q_BW, true, false, false);  // both K-major
         uint32_t it = 0;
         int gi = 0;
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
@@ -186,7 +187,7 @@ k_local_attn_bwd_q_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
             mbar_wait(&info_full[gi % Q_NINFO], (gi / Q_NINFO) & 1, 0x030500, gi);
             const GroupInfo inf = infos[gi % Q_NINFO];
             for (int cb = 0; cb < inf.ncb; ++cb) {
-                const int C0 = inf.x0 + cb * BW;
+                const int C0 = inf.x0 + cb * Q_BW;
                 for (int rc = 0; rc < inf.nrc; ++rc, ++it) {
                     const int buf = it % Q_NACC, R0 = inf.y0 + rc * Q_ROWS;
                     mbar_wait(&acc_full[buf], (it / Q_NACC) & 1, 0x030300 | buf, it);
@@ -212,7 +213,7 @@ k_local_attn_bwd_q_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
 #pragma unroll
                                 for (int c = 0; c < K1; ++c) {
                                     const int e = clampi(X0 + c, Ws - 1) - C0;
-                                    if (e >= 0 && e < BW) Qw[r * K1 + c] = v[rr * BW + e];   // dynamic index: v lives in local memory
+                                    if (e >= 0 && e < Q_BW) Qw[r * K1 + c] = v[rr * Q_BW + e];   // dynamic index: v lives in local memory
                                 }
                             }
                         }
@@ -314,7 +315,7 @@ static int launch_q(const void* src, const void* flow, const void* logits, const
     {
         const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)B};
         const cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)Ws * C * 2, (cuuint64_t)Hs * Ws * C * 2};
-        const cuuint32_t box[4] = {64, BW, Q_ROWS, 1};
+        const cuuint32_t box[4] = {64, Q_BW, Q_ROWS, 1};
         if (enc(&ts, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), gdim, gstr, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
