@@ -37,6 +37,7 @@ struct RsTaps {
     A xL_[NT], xR_[NT], yT_[NT], yB_[NT];          // distances
     A xL_P[NT], xR_P[NT], yT_P[NT], yB_P[NT];      // Gaussian factors (depend on fx resp. fy only)
     A sigma;
+    int flx, fly;           // floor(x + dx), floor(y + dy)
 };
 
 template <typename A, int NT>
@@ -49,6 +50,8 @@ __device__ __forceinline__ void rs_setup(RsTaps<A, NT>& t, const A* __restrict__
     const A xf = static_cast<A>(x) + dx, yf = static_cast<A>(y) + dy;
     const A alpha = trunc_frac ? xf - static_cast<A>(static_cast<int>(xf)) : xf - flr(xf);
     const A beta = trunc_frac ? yf - static_cast<A>(static_cast<int>(yf)) : yf - flr(yf);
+    t.flx = static_cast<int>(flr(xf));
+    t.fly = static_cast<int>(flr(yf));
     const A two_s2 = 2 * t.sigma * t.sigma;
 #pragma unroll
     for (int f = 0; f < NT; ++f) {
@@ -120,13 +123,19 @@ k_resample2d_fwd(const A* __restrict__ in1, const A* __restrict__ in2, A* __rest
     }
 }
 
+// grad_input1: a scatter of 4*(ks/2)^2 weighted copies of grad_out per (pixel, channel).  When the 32 pixels of a
+// warp are a run of one image row whose taps are the same integer shift (the usual case for a smooth flow) and no
+// tap is clamped, lane L's contribution to column (x_L + shift + co) is exactly what lane L+co accumulates for its
+// own centre column: the (2*ks/2)^2 scalar atomics per element collapse to one red.global per tap ROW per lane
+// (plus the few taps that leave the warp's 32 columns) after a register-level exchange with __shfl_sync.
 template <typename A, int NT>
 __global__ void __launch_bounds__(128)
 k_resample2d_bwd_in1(const A* __restrict__ in2, const A* __restrict__ gout, A* __restrict__ gin1, int B, int C, int Hi,
-                     int Wi, int H, int W, int dil, int c_per_slice) {
+                     int Wi, int H, int W, int dil, int c_per_slice, int warp_rows) {
     const long long total = (long long)B * H * W;
-    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= total) return;
+    const long long pix_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = pix_raw < total;
+    const long long pix = active ? pix_raw : total - 1;   // inactive lanes stay alive for the warp shuffles
     const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
     RsTaps<A, NT> t;
     rs_setup<A, NT>(t, in2, b, y, x, H, W, Hi, Wi, dil, true);  // truncating fraction for the weights
@@ -144,6 +153,51 @@ k_resample2d_bwd_in1(const A* __restrict__ in2, const A* __restrict__ gout, A* _
     const int c0 = blockIdx.y * c_per_slice, c1 = min(C, c0 + c_per_slice);
     A* gi = gin1 + ((long long)b * C + c0) * ipl;
     const A* go = gout + ((long long)b * C + c0) * opl + (long long)y * W + x;
+
+    bool fast = false;
+    if (NT <= 2) {
+        const unsigned full = 0xffffffffu;
+        bool ok = active && warp_rows && dil == 1 && t.flx - (NT - 1) >= 0 && t.flx + NT <= Wi - 1 &&
+                  t.fly - (NT - 1) >= 0 && t.fly + NT <= Hi - 1;
+        const int shift = t.flx - x;
+        ok = ok && shift == __shfl_sync(full, shift, 0) && t.fly == __shfl_sync(full, t.fly, 0);
+        fast = __all_sync(full, ok);
+    }
+    if (fast) {
+        constexpr int N2 = 2 * NT;   // taps per axis: offsets -(NT-1) .. NT around (fly, flx)
+        const unsigned full = 0xffffffffu;
+        const int lane = threadIdx.x & 31;
+        double wg[N2 * N2];          // weight of (row offset ri-(NT-1), column offset ci-(NT-1))
+#pragma unroll
+        for (int fy = 0; fy < NT; ++fy)
+#pragma unroll
+            for (int fx = 0; fx < NT; ++fx) {
+                const double* q = wn + (fy * NT + fx) * 4;
+                wg[(NT - 1 - fy) * N2 + (NT - 1 - fx)] = q[0];   // yT, xL
+                wg[(NT - 1 - fy) * N2 + (NT + fx)] = q[1];       // yT, xR
+                wg[(NT + fy) * N2 + (NT - 1 - fx)] = q[2];       // yB, xL
+                wg[(NT + fy) * N2 + (NT + fx)] = q[3];           // yB, xR
+            }
+        const int centre = (t.fly - (NT - 1)) * Wi + t.flx;      // first tap row, this lane's centre column
+        for (int c = c0; c < c1; ++c, gi += ipl, go += opl) {
+            const double g = static_cast<double>(*go);
+#pragma unroll
+            for (int ri = 0; ri < N2; ++ri) {
+                A acc = static_cast<A>(0);
+#pragma unroll
+                for (int ci = 0; ci < N2; ++ci) {
+                    const int co = ci - (NT - 1);
+                    const A v = static_cast<A>(wg[ri * N2 + ci] * g);
+                    const A recv = __shfl_sync(full, v, (lane - co) & 31);   // what lane - co sends to column offset co = me
+                    if (lane - co >= 0 && lane - co < 32) acc += recv;
+                    if (lane + co < 0 || lane + co > 31) atomicAdd(gi + centre + ri * Wi + co, v);   // leaves the warp's span
+                }
+                atomicAdd(gi + centre + ri * Wi, acc);
+            }
+        }
+        return;
+    }
+    if (!active) return;
 #pragma unroll 4
     for (int c = c0; c < c1; ++c, gi += ipl, go += opl) {
         const double g = static_cast<double>(*go);
@@ -227,7 +281,8 @@ static int rs_launch_bwd(const void* in1, const void* in2, const void* gout, voi
     const long long total = (long long)B * H * W;
     const int threads = 128, slices0 = channel_splits(total, C, threads), cps = (C + slices0 - 1) / slices0;
     dim3 grid((unsigned)((total + threads - 1) / threads), (unsigned)((C + cps - 1) / cps));
-    k_resample2d_bwd_in1<A, NT><<<grid, threads, 0, st_>>>((const A*)in2, (const A*)gout, (A*)gin1, B, C, Hi, Wi, H, W, dil, cps);
+    k_resample2d_bwd_in1<A, NT><<<grid, threads, 0, st_>>>((const A*)in2, (const A*)gout, (A*)gin1, B, C, Hi, Wi, H, W, dil, cps,
+                                                           (W % 32 == 0) ? 1 : 0);
     int e = launch_status();
     if (e) return e;
     k_resample2d_bwd_in2<A, NT><<<(unsigned)((total + threads - 1) / threads), threads, 0, st_>>>(

@@ -652,3 +652,27 @@ def test_block_extractor_bf16_backward_fp32_accumulation(F_, oracle_lib):
     ogs, ogf = oracle_lib.block_extract_bwd(host(s), f.cpu().numpy(), host(g), k)
     np.testing.assert_allclose(host(gs), ogs, rtol=1e-2, atol=1e-2 * max(1.0, float(np.abs(ogs).max())))
     np.testing.assert_allclose(host(gf), ogf, rtol=1e-3, atol=1e-3 * max(1.0, float(np.abs(ogf).max())))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("cfg", [(2, 5.0, "uniform"), (4, 2.0, "uniform"), (4, 2.0, "mixed"), (2, 5.0, "border")])
+def test_resample2d_backward_warp_merged_scatter(F_, oracle_lib, dt, cfg):
+    """grad_input1 with W % 32 == 0: warps whose 32 pixels share one integer tap shift merge their scatter through
+    shuffles (one red per tap row); the others (and clamped taps) keep the scalar path.  Both against the oracle."""
+    ks, sigma, kind = cfg
+    rng = np.random.default_rng(ks + len(kind))
+    B, C, H, W = 2, 5, 9, 64
+    a = rng.standard_normal((B, C, H, W)).astype(dt)
+    if kind == "uniform":      # floor(x + dx) - x == 2, floor(y + dy) - y == -1 everywhere (interior rows only matter)
+        fl = np.stack([2.2 + 0.6 * rng.random((B, H, W)), -0.9 + 0.8 * rng.random((B, H, W))], 1)
+    elif kind == "mixed":      # shift changes in the middle of some rows
+        fl = np.stack([np.where(np.arange(W)[None, None, :] < 40, 1.3, 2.6) + 0.2 * rng.random((B, H, W)),
+                       0.4 * rng.random((B, H, W))], 1)
+    else:                      # taps clamped at the image border
+        fl = np.stack([np.full((B, H, W), 7.5) * np.sign(rng.standard_normal((B, H, 1))), rng.uniform(-6, 6, (B, H, W))], 1)
+    in2 = np.ascontiguousarray(np.concatenate([fl, np.full((B, 1, H, W), sigma)], 1).astype(dt))
+    g = rng.standard_normal((B, C, H, W)).astype(dt)
+    g1, g2 = F_.resample2d_bwd(cu(a), cu(in2), cu(g), ks, 1)
+    o1, o2 = oracle_lib.resample2d_bwd(a, in2, g, ks, 1)
+    t = tol(dt, 1e-5, 1e-12)
+    np.testing.assert_allclose(host(g1), o1, rtol=t, atol=t * max(1.0, float(np.abs(o1).max())))
