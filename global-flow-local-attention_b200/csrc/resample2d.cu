@@ -160,7 +160,10 @@ k_resample2d_bwd_in1(const A* __restrict__ in2, const A* __restrict__ gout, A* _
         bool ok = active && warp_rows && dil == 1 && t.flx - (NT - 1) >= 0 && t.flx + NT <= Wi - 1 &&
                   t.fly - (NT - 1) >= 0 && t.fly + NT <= Hi - 1;
         const int shift = t.flx - x;
-        ok = ok && shift == __shfl_sync(full, shift, 0) && t.fly == __shfl_sync(full, t.fly, 0);
+        // warp-collective: every lane executes the shuffles (no short-circuit in front of them)
+        const int shift0 = __shfl_sync(full, shift, 0);
+        const int fly0 = __shfl_sync(full, t.fly, 0);
+        ok = ok && (shift == shift0) && (t.fly == fly0);
         fast = __all_sync(full, ok);
     }
     if (fast) {
