@@ -31,14 +31,19 @@ if "cfg3" in which:   # resample2d fwd+bwd, B=32 C=128 512x512 fp32 (BASELINE.js
     B, C, H, W = 32, 128, 512, 512
     x = torch.randn(B, C, H, W, device=dev)
     g = torch.randn(B, C, H, W, device=dev)
+    # "blocky" = nearest-neighbour x16 up-sampling of a coarse flow + sub-pixel jitter, the shape PerceptualCorrectness feeds
+    # (external_function.py:243: F.interpolate(flow, [h, w]), default mode 'nearest'): constant integer tap shift per block
+    coarse = (torch.rand(B, 2, H // 16, W // 16, device=dev) * 16 - 8).floor() + 0.25
+    blocky = (torch.nn.functional.interpolate(coarse, size=(H, W), mode="nearest") + 0.5 * torch.rand(B, 2, H, W, device=dev)).contiguous()
     for ks, sigma in ((2, 5.0), (4, 2.0)):
-        in2 = torch.cat([smooth(B, H, W), torch.full((B, 1, H, W), sigma, device=dev)], 1).contiguous()
         px = B * H * W
-        f = timed(lambda: F_.resample2d_fwd(x, in2, ks, 1))
-        b = timed(lambda: F_.resample2d_bwd(x, in2, g, ks, 1), n=3, w=1)
-        emit(f"resample2d_fwd ks={ks}", f, px, px * (2 * C * 4 + 12), config="cfg3 B=32 C=128 512x512 fp32")
-        emit(f"resample2d_bwd ks={ks}", b, px, px * (3 * C * 4 + 24), config="cfg3")
-        emit(f"resample2d_fwd+bwd ks={ks}", f + b, px, px * (5 * C * 4 + 36), config="cfg3")
+        for fname, fl in (("smooth", smooth(B, H, W)), ("blocky", blocky)):
+            in2 = torch.cat([fl, torch.full((B, 1, H, W), sigma, device=dev)], 1).contiguous()
+            f = timed(lambda: F_.resample2d_fwd(x, in2, ks, 1))
+            b = timed(lambda: F_.resample2d_bwd(x, in2, g, ks, 1), n=3, w=1)
+            emit(f"resample2d_fwd ks={ks} {fname} flow", f, px, px * (2 * C * 4 + 12), config="cfg3 B=32 C=128 512x512 fp32")
+            emit(f"resample2d_bwd ks={ks} {fname} flow", b, px, px * (3 * C * 4 + 24), config="cfg3")
+            emit(f"resample2d_fwd+bwd ks={ks} {fname} flow", f + b, px, px * (5 * C * 4 + 36), config="cfg3")
 if "cfg2_unfused" in which:   # the unfused ops at cfg2-like size (B=2: the [B,C,kH,kW] block tensor is 25x the input)
     B, C, H, W, k = 2, 256, 256, 256, 5
     s = torch.randn(B, C, H, W, device=dev).bfloat16(); fl = smooth(B, H, W)
