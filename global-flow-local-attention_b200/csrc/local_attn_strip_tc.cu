@@ -1,0 +1,413 @@
+// Fused local-attention FORWARD, channels-last, "strip" schedule (tcgen05 + TMEM + TMA).
+//
+// Same GEMM embedding as local_attn_tc.cu (16x8 pixel tile = M, channels = N, footprint positions = K,
+// A = per-pixel weight slabs built on the fly, B = source rows by TMA, D in TMEM), different traversal:
+// local_attn_tc.cu treats every tile on its own and pulls its whole (k + flow variation)-row footprint
+// through the L2->SM fabric, ~4.3 source positions per output pixel -- and that fabric, not HBM, is what
+// bounds the kernel.  Here a CTA owns a vertical run of tiles; a source row chunk
+// that the current tile loads and the next tile also needs is multiplied into BOTH accumulators while it
+// sits in shared memory (two weight slabs, one B operand), so in steady state a tile fetches only the
+// ~8 rows its predecessor did not already see.  The schedule is in strip_plan.h.
+//
+// Warp roles (10 warps, persistent CTA, static round-robin over strips):
+//   warp 0      producer: tile bounding boxes, step schedule, TMA row loads;
+//   warp 1      MMA issuer: per step one MMA set per consuming tile (accumulators alternate between the
+//               two TMEM halves; the next tile's half is claimed at its first shared step);
+//   warps 2-5   builders: softmax + tap arithmetic + window collapse for the current AND the next tile,
+//               one weight slab per (step, consuming tile);
+//   warps 6-9   epilogue: TMEM -> bf16 -> 64-byte channels-last stores (optional mask blend), literal
+//               4-tap recomputation of the irregular pixels (bit-identical indexing).
+#include "strip_plan.h"
+#include "tile_window.cuh"
+
+namespace gfla {
+
+namespace tc {
+
+constexpr int ST_RCH = 2;        // source rows per step (fixed by strip_plan.h: chunk j = rows 2j, 2j+1)
+constexpr int ST_FBW = 32;       // source positions per row segment
+constexpr int ST_NINFO = 8;      // >= stages + 3: every tile pass has at least one step (strip_plan), so the
+                                 // producer is never more than `stages` tiles ahead of the builders / MMA warp
+constexpr int ST_THREADS = 320;
+
+template <int CN>
+struct StripSmem {
+    static constexpr int NSTAGE = CN == 256 ? 3 : 4;
+    static constexpr int S_SLAB = CN * ST_FBW * 2;             // one source row segment: [CN/64][32 x][64 ch] bf16
+    static constexpr int FA_SLAB = 128 * ST_FBW * 2;           // weight slab: [128 pixels][32 positions] bf16
+    static constexpr int S_STAGE = ST_RCH * S_SLAB;
+    static constexpr int A_TILE = ST_RCH * FA_SLAB;            // the slabs of one consuming tile
+    static constexpr int A_STAGE = 2 * A_TILE;                 // current tile, next tile
+    static constexpr int W_TILE = 36 * 128 * 2;                // collapsed windows of one tile, [18 words][128 pixels]
+    static constexpr int OFF_S = 0;
+    static constexpr int OFF_A = OFF_S + NSTAGE * S_STAGE;
+    static constexpr int OFF_W = OFF_A + NSTAGE * A_STAGE;
+    static constexpr int OFF_INFO = OFF_W + 2 * W_TILE;
+    static constexpr int OFF_BAR = OFF_INFO + ST_NINFO * 32;
+    static constexpr int NBAR = 3 * NSTAGE + 4 + ST_NINFO;
+    static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+    static constexpr int TOTAL = OFF_TMEM + 16;
+    static constexpr int ALLOC = TOTAL + 1024;                 // slack to align the base to 1024 B
+};
+static_assert(sizeof(StripTile) == 32, "StripTile is stored in 32-byte info slots");
+static_assert(StripSmem<256>::ALLOC <= 232448, "shared memory budget");
+
+// strips: units of `ts` vertically adjacent tiles; unit -> (b, gx, first tile row, end tile row)
+struct StripGeom {
+    int gxn, gyn, nseg, ts, units;
+    __device__ __forceinline__ void decode(int unit, int& b, int& gx, int& ty0, int& ty1) const {
+        gx = unit % gxn;
+        const int seg = (unit / gxn) % nseg;
+        b = unit / (gxn * nseg);
+        ty0 = seg * ts;
+        ty1 = min(gyn, ty0 + ts);
+    }
+};
+
+template <int K, int CN>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfloat16* __restrict__ src,
+                       const float* __restrict__ flow, const __nv_bfloat16* __restrict__ logits,
+                       __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ probs,
+                       const __nv_bfloat16* __restrict__ prev, const __nv_bfloat16* __restrict__ mask, int B, int C, int Hs,
+                       int Ws, int H, int W, int ts) {
+    using SM = StripSmem<CN>;
+    constexpr int NSTAGE = SM::NSTAGE, FBW = ST_FBW, RCH = ST_RCH;
+    constexpr int K1 = K + 1, KK = K * K;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
+    uint64_t* full_s = bars;                      // [NSTAGE] TMA bytes landed
+    uint64_t* full_a = bars + NSTAGE;             // [NSTAGE] 128 builder arrivals
+    uint64_t* empty = bars + 2 * NSTAGE;          // [NSTAGE] MMAs of the stage retired
+    uint64_t* acc_full = bars + 3 * NSTAGE;       // [2]
+    uint64_t* acc_empty = bars + 3 * NSTAGE + 2;  // [2]
+    uint64_t* info_full = bars + 3 * NSTAGE + 4;  // [ST_NINFO]
+    StripTile* infos = reinterpret_cast<StripTile*>(smem + SM::OFF_INFO);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_TMEM);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    StripGeom geo;
+    geo.gxn = (W + GW - 1) / GW;
+    geo.gyn = (H + GH - 1) / GH;
+    geo.ts = ts;
+    geo.nseg = (geo.gyn + ts - 1) / ts;
+    geo.units = B * geo.gxn * geo.nseg;
+    const int c0 = blockIdx.y * CN;
+    const long long hw = (long long)H * W;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full_s[i], 1); mbar_init(&full_a[i], 128); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < ST_NINFO; ++i) mbar_init(&info_full[i], 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmap_src);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * CN >= 32 ? 2 * CN : 32);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================================= producer
+        uint32_t it = 0;  // global step counter
+        int ti = 0;       // global tile counter of this CTA
+        for (int unit = blockIdx.x; unit < geo.units; unit += gridDim.x) {
+            int b, gx, ty0, ty1;
+            geo.decode(unit, b, gx, ty0, ty1);
+            TileBox cur, nxt = TileBox{0, 0, 0, 0};
+            group_bbox<K>(flow, b, gx * GW, ty0 * GH, H, W, Hs, Ws, lane, false, cur.x0, cur.y0, cur.x1, cur.y1);
+            int k0 = 1, k1 = 0;
+            for (int ty = ty0; ty < ty1; ++ty, ++ti) {
+                const bool has_next = ty + 1 < ty1;
+                if (has_next) group_bbox<K>(flow, b, gx * GW, (ty + 1) * GH, H, W, Hs, Ws, lane, false, nxt.x0, nxt.y0, nxt.x1, nxt.y1);
+                const StripTile t = strip_plan(cur, has_next, nxt, k0, k1, FBW);
+                if (lane == 0) {
+                    infos[ti % ST_NINFO] = t;
+                    mbar_arrive(&info_full[ti % ST_NINFO]);
+                }
+                for (int cb = 0; cb < t.ncb; ++cb)
+                    for (int j = t.j0; j <= t.j1; ++j) {
+                        if (strip_skipped(t, j)) continue;
+                        const int slot = it % NSTAGE;
+                        mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x000200 | slot, it);
+                        if (lane == 0) {
+                            mbar_arrive_expect_tx(&full_s[slot], SM::S_STAGE);
+#pragma unroll
+                            for (int rr = 0; rr < RCH; ++rr) {
+                                uint8_t* dst = smem + SM::OFF_S + slot * SM::S_STAGE + rr * SM::S_SLAB;
+#pragma unroll
+                                for (int cg = 0; cg < CN / 64; ++cg)   // [CN/64 channel groups][FBW x][64 channels]
+                                    tma_load_4d(dst + cg * (FBW * 128), &tmap_src, &full_s[slot], c0 + cg * 64, t.xs + cb * FBW,
+                                                2 * j + rr, b);
+                            }
+                        }
+                        __syncwarp();
+                        ++it;
+                    }
+                k0 = t.s0; k1 = t.s1;
+                cur = nxt;
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer
+        constexpr uint32_t idesc = make_idesc_f16(128, CN, true, false, true);
+        uint32_t it = 0;
+        int ti = 0;
+        for (int unit = blockIdx.x; unit < geo.units; unit += gridDim.x) {
+            int b, gx, ty0, ty1;
+            geo.decode(unit, b, gx, ty0, ty1);
+            bool started = false;   // this tile's accumulator already holds the previous pass's shared steps
+            for (int ty = ty0; ty < ty1; ++ty, ++ti) {
+                mbar_wait(&info_full[ti % ST_NINFO], (ti / ST_NINFO) & 1, 0x010500, ti);
+                const StripTile t = infos[ti % ST_NINFO];
+                const int buf = ti & 1;
+                bool next_started = false;
+                for (int cb = 0; cb < t.ncb; ++cb)
+                    for (int j = t.j0; j <= t.j1; ++j) {
+                        if (strip_skipped(t, j)) continue;
+                        const bool shared = strip_shared(t, j);
+                        if (!started) {   // first touch of this tile's TMEM half: its previous user must be drained
+                            mbar_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1, 0x010400 | buf, ti);
+                            tc_fence_after();
+                        }
+                        if (shared && !next_started) {
+                            mbar_wait(&acc_empty[buf ^ 1], (((ti + 1) >> 1) & 1) ^ 1, 0x010600 | (buf ^ 1), ti);
+                            tc_fence_after();
+                        }
+                        const int slot = it % NSTAGE;
+                        const uint32_t par = (it / NSTAGE) & 1;
+                        mbar_wait(&full_s[slot], par, 0x010000 | slot, it);
+                        mbar_wait(&full_a[slot], par, 0x010100 | slot, it);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint32_t a0 = smem_u32(smem + SM::OFF_A + slot * SM::A_STAGE);
+                            const uint32_t b0 = smem_u32(smem + SM::OFF_S + slot * SM::S_STAGE);
+#pragma unroll
+                            for (int sub = 0; sub < 2; ++sub) {
+                                if (sub == 1 && !shared) break;
+                                const uint32_t d_tmem = tmem_base + (sub == 0 ? buf : (buf ^ 1)) * CN;
+                                const bool fresh = sub == 0 ? !started : !next_started;
+#pragma unroll
+                                for (int rr = 0; rr < RCH; ++rr)
+#pragma unroll
+                                    for (int h = 0; h < FBW / 16; ++h) {  // K = 16 positions per MMA
+                                        // A = [128 px][32 pos], K-major, 64B rows, 64B swizzle; K-advance = +32 B
+                                        const uint64_t ad = make_smem_desc(a0 + sub * SM::A_TILE + rr * SM::FA_SLAB + h * 32, 16, 512, kSwizzle64);
+                                        // B = [32 x][64 ch] per channel group, MN-major, 128B swizzle: LBO = next channel group,
+                                        // SBO = next 8 positions (1 KB); K-advance = 2 KB
+                                        const uint64_t bd = make_smem_desc(b0 + rr * SM::S_SLAB + h * 2048, FBW * 128, 1024, kSwizzle128);
+                                        umma_f16(d_tmem, ad, bd, idesc, (fresh && rr == 0 && h == 0) ? 0u : 1u);
+                                    }
+                            }
+                            tc_commit(&empty[slot]);
+                        }
+                        __syncwarp();
+                        started = true;
+                        if (shared) next_started = true;
+                        ++it;
+                    }
+                if (lane == 0) tc_commit(&acc_full[buf]);
+                __syncwarp();
+                started = next_started;
+            }
+        }
+    } else if (warp < 6) {
+        // ================================================================= builders
+        const int q = warp & 3, m = q * 32 + lane;  // pixel index inside a tile
+        const float inv_kk = 1.0f / static_cast<float>(KK);
+        const uint32_t wsm_base = smem_u32(smem + SM::OFF_W) + m * 4;           // + (tile parity) * W_TILE
+        const uint32_t a_base = smem_u32(smem + SM::OFF_A) + m * (FBW * 2);     // this pixel's row in slab 0
+        const uint32_t swz = ((m >> 1) & 3) << 4;                               // 64B-swizzle XOR of this row's 16B chunks
+        uint32_t it = 0, dirty = 0xffffffffu;   // slab rows start with unknown contents: treat them as dirty
+        int ti = 0;
+        // collapsed window of pixel m of tile (b, gx, ty) -> shared memory; returns whether the pixel is regular
+        auto make_window = [&](int b, int gx, int ty, uint32_t wsm_a, int& X0, int& Y0) -> bool {
+            const int px = gx * GW + (m & 15), py = ty * GH + (m >> 4);
+            X0 = 0; Y0 = 0;
+            if (!(px < W && py < H)) return false;
+            const long long pofs = (long long)py * W + px;
+            float p[KK];
+            pixel_softmax_f32<KK>(logits + (long long)b * KK * hw + pofs, hw, p);
+            if (probs != nullptr && blockIdx.y == 0) {
+                __nv_bfloat16* pr = probs + (long long)b * KK * hw + pofs;
+#pragma unroll
+                for (int t = 0; t < KK; ++t) pr[t * hw] = __float2bfloat16_rn(p[t]);
+            }
+            const float fx = flow[(long long)b * 2 * hw + pofs], fy = flow[(long long)b * 2 * hw + hw + pofs];
+            AxisTap<float> tx[K], ty_[K];
+            if (!taps_regular<K>(fx, fy, px, py, Hs, Ws, tx, ty_)) return false;
+            float w[K1 * K1];
+            build_window<K>(p, tx, ty_, Hs, Ws, inv_kk, w, X0, Y0);
+            store_window_words<K>(wsm_a, w);
+            return true;
+        };
+        for (int unit = blockIdx.x; unit < geo.units; unit += gridDim.x) {
+            int b, gx, ty0, ty1;
+            geo.decode(unit, b, gx, ty0, ty1);
+            int X0 = 0, Y0 = 0, nX0 = 0, nY0 = 0;
+            bool live = false, nlive = false, have = false;   // have: this tile's window was built during the previous pass
+            for (int ty = ty0; ty < ty1; ++ty, ++ti) {
+                const uint32_t wsm_cur = wsm_base + (ti & 1) * SM::W_TILE, wsm_nxt = wsm_base + ((ti + 1) & 1) * SM::W_TILE;
+                if (have) { X0 = nX0; Y0 = nY0; live = nlive; }
+                else live = make_window(b, gx, ty, wsm_cur, X0, Y0);
+                mbar_wait(&info_full[ti % ST_NINFO], (ti / ST_NINFO) & 1, 0x020500, ti);
+                const StripTile t = infos[ti % ST_NINFO];
+                have = t.s0 <= t.s1;
+                if (have) nlive = make_window(b, gx, ty + 1, wsm_nxt, nX0, nY0);
+                for (int cb = 0; cb < t.ncb; ++cb) {
+                    const int e0 = X0 - (t.xs + cb * FBW), e0n = nX0 - (t.xs + cb * FBW);   // box position of window column 0
+                    const bool cols_hit = live && e0 > -K1 && e0 < FBW;
+                    const bool cols_hit_n = have && nlive && e0n > -K1 && e0n < FBW;
+                    for (int j = t.j0; j <= t.j1; ++j) {
+                        if (strip_skipped(t, j)) continue;
+                        const int slot = it % NSTAGE;
+                        mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x020200 | slot, it);
+                        const uint32_t a_stage = a_base + slot * SM::A_STAGE;
+                        const int R0 = 2 * j;
+                        bool wrote = false;
+#pragma unroll
+                        for (int rr = 0; rr < RCH; ++rr)
+                            wrote |= fill_slab_row<K, FBW>(a_stage + rr * SM::FA_SLAB, swz, wsm_cur, cols_hit, (R0 + rr) - Y0, e0, dirty,
+                                                      1u << ((slot * RCH + rr) * 2));
+                        if (strip_shared(t, j)) {
+#pragma unroll
+                            for (int rr = 0; rr < RCH; ++rr)
+                                wrote |= fill_slab_row<K, FBW>(a_stage + SM::A_TILE + rr * SM::FA_SLAB, swz, wsm_nxt, cols_hit_n,
+                                                          (R0 + rr) - nY0, e0n, dirty, 1u << ((slot * RCH + rr) * 2 + 1));
+                        }
+                        if (wrote) fence_proxy_async_smem();
+                        mbar_arrive(&full_a[slot]);
+                        ++it;
+                    }
+                }
+            }
+        }
+    } else {
+        // ================================================================= epilogue
+        const int q = warp & 3, m = q * 32 + lane;
+        int ti = 0;
+        for (int unit = blockIdx.x; unit < geo.units; unit += gridDim.x) {
+            int b, gx, ty0, ty1;
+            geo.decode(unit, b, gx, ty0, ty1);
+            for (int ty = ty0; ty < ty1; ++ty, ++ti) {
+                const int px = gx * GW + (m & 15), py = ty * GH + (m >> 4);
+                const bool valid = px < W && py < H;
+                const long long pofs = (long long)py * W + px;
+                bool regular = false;
+                float fx = 0.f, fy = 0.f;
+                if (valid) {
+                    fx = flow[(long long)b * 2 * hw + pofs];
+                    fy = flow[(long long)b * 2 * hw + hw + pofs];
+                    AxisTap<float> tx[K], ty_[K];
+                    regular = taps_regular<K>(fx, fy, px, py, Hs, Ws, tx, ty_);
+                }
+                const int buf = ti & 1;
+                mbar_wait(&acc_full[buf], (ti >> 1) & 1, 0x030300 | buf, ti);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * CN;
+                __nv_bfloat16* o = out + ((long long)b * hw + pofs) * C + c0;
+                // optional fused mask blend (generator.py:130): out = prev * (1 - mask) + attention * mask
+                const __nv_bfloat16* pv = prev == nullptr ? nullptr : prev + ((long long)b * hw + pofs) * C + c0;
+                const float mk = (prev != nullptr && valid) ? __bfloat162float(mask[(long long)b * hw + pofs]) : 1.f;
+#pragma unroll 1
+                for (int cc = 0; cc < CN / 32; ++cc) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + cc * 32, v);
+                    tmem_ld_wait();
+                    if (valid && regular) {
+                        if (pv != nullptr) {   // blend in fp32 before the single rounding to bf16
+                            const uint4* p4 = reinterpret_cast<const uint4*>(pv + cc * 32);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const uint4 pq = p4[i];
+                                const uint32_t pw[4] = {pq.x, pq.y, pq.z, pq.w};
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj) {
+                                    const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pw[jj]));
+                                    v[8 * i + 2 * jj] = __float_as_uint(pf.x * (1.f - mk) + __uint_as_float(v[8 * i + 2 * jj]) * mk);
+                                    v[8 * i + 2 * jj + 1] = __float_as_uint(pf.y * (1.f - mk) + __uint_as_float(v[8 * i + 2 * jj + 1]) * mk);
+                                }
+                            }
+                        }
+                        uint4* o4 = reinterpret_cast<uint4*>(o + cc * 32);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            uint4 pk;
+                            __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
+                            __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
+                            __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
+                            __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+                            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                            __stcs(o4 + i, pk);   // streaming store: written once, never re-read by this kernel
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                // irregular pixels (fp32 rounding of (flow+offset)+coord straddling an integer, ~1e-5 of all pixels): the
+                // reference's literal 4-taps-per-(i,j) arithmetic, the warp shares one pixel (lanes split the channels)
+                unsigned todo = __ballot_sync(0xffffffffu, valid && !regular);
+                while (todo) {
+                    const int src_lane = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int qx = __shfl_sync(0xffffffffu, px, src_lane), qy = __shfl_sync(0xffffffffu, py, src_lane);
+                    const float qfx = __shfl_sync(0xffffffffu, fx, src_lane), qfy = __shfl_sync(0xffffffffu, fy, src_lane);
+                    irregular_pixel<K, true>(src, logits, out, prev, mask, b, C, c0, CN, Hs, Ws, H, W, qx, qy, qfx, qfy, lane);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * CN >= 32 ? 2 * CN : 32);
+}
+
+template <int K, int CN>
+static int launch_strip(const void* src, const void* flow, const void* logits, void* out, void* probs, const void* prev,
+                        const void* mask, int B, int C, int Hs, int Ws, int H, int W, int ts, cudaStream_t st_) {
+    static const PFN_tmapEncodeTiled enc = tmap_encoder();
+    if (enc == nullptr) return GFLA_E_NOTSUP;
+    CUtensorMap tmap;
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    // (c, x, y, b), box [64 c][32 x]: 128-byte runs, 128B swizzle
+    const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)B};
+    const cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)Ws * C * 2, (cuuint64_t)Hs * Ws * C * 2};
+    const cuuint32_t box[4] = {64, ST_FBW, 1, 1};
+    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return GFLA_E_NOTSUP;
+    auto kern = k_local_attn_fwd_strip<K, CN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, StripSmem<CN>::ALLOC);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const int gxn = (W + GW - 1) / GW, gyn = (H + GH - 1) / GH;
+    if (ts <= 0) {   // longest strips that still leave every SM several units to balance the tail
+        ts = 8;
+        while (ts > 1 && (long long)B * gxn * ((gyn + ts - 1) / ts) < 4LL * sm_count()) ts >>= 1;
+    }
+    const int units = B * gxn * ((gyn + ts - 1) / ts);
+    dim3 grid((unsigned)min(units, sm_count()), (unsigned)(C / CN));
+    kern<<<grid, ST_THREADS, StripSmem<CN>::ALLOC, st_>>>(tmap, (const __nv_bfloat16*)src, (const float*)flow,
+                                                          (const __nv_bfloat16*)logits, (__nv_bfloat16*)out, (__nv_bfloat16*)probs,
+                                                          (const __nv_bfloat16*)prev, (const __nv_bfloat16*)mask, B, C, Hs, Ws, H, W, ts);
+    return launch_status();
+}
+
+}  // namespace tc
+
+// channels-last only; same eligibility as local_attn_fwd_tc (checked by the caller).  ts = tiles per strip, 0 = automatic.
+int local_attn_fwd_strip_tc(const void* src, const void* flow, const void* logits, void* out, void* probs, const void* prev,
+                            const void* mask, int B, int C, int Hs, int Ws, int H, int W, int k, int ts, cudaStream_t st_) {
+    const int cn = (C % 256 == 0) ? 256 : C;
+#define GFLA_STRIP_CASE(K_, CN_) \
+    if (k == K_ && cn == CN_) return tc::launch_strip<K_, CN_>(src, flow, logits, out, probs, prev, mask, B, C, Hs, Ws, H, W, ts, st_);
+    GFLA_STRIP_CASE(5, 256) GFLA_STRIP_CASE(5, 128) GFLA_STRIP_CASE(5, 64)
+    GFLA_STRIP_CASE(3, 256) GFLA_STRIP_CASE(3, 128) GFLA_STRIP_CASE(3, 64)
+#undef GFLA_STRIP_CASE
+    return GFLA_E_NOTSUP;
+}
+
+}  // namespace gfla

@@ -348,50 +348,14 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            // Pixels whose taps are not consecutive integers (fp32 rounding of (flow+offset)+coord straddling an
-            // integer: ~1e-5 of all pixels) keep the reference's literal 4-taps-per-(i,j) arithmetic.  One such pixel
-            // costs 100*CN dependent loads, so the whole warp shares it: lanes split the channels.
+            // irregular pixels keep the reference's literal 4-tap arithmetic; the warp shares each one (tile_window.cuh)
             unsigned todo = __ballot_sync(0xffffffffu, valid && !regular);
             while (todo) {
                 const int src_lane = __ffs(todo) - 1;
                 todo &= todo - 1;
                 const int qx = __shfl_sync(0xffffffffu, px, src_lane), qy = __shfl_sync(0xffffffffu, py, src_lane);
                 const float qfx = __shfl_sync(0xffffffffu, fx, src_lane), qfy = __shfl_sync(0xffffffffu, fy, src_lane);
-                const long long qofs = (long long)qy * W + qx;
-                float p[KK];
-                pixel_softmax_f32<KK>(logits + (long long)b * KK * hw + qofs, hw, p);   // every lane: same loads (broadcast)
-                AxisTap<float> tx[K], ty[K];
-#pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    tx[j] = axis_tap<float>(qfx, j - K / 2, qx, Ws);
-                    ty[j] = axis_tap<float>(qfy, j - K / 2, qy, Hs);
-                }
-                const long long spl = (long long)Hs * Ws;
-                const long long sc = NHWC ? 1 : spl, sp = NHWC ? C : 1;     // element strides: channel, position
-                const __nv_bfloat16* sb = NHWC ? src + (long long)b * spl * C + c0 : src + ((long long)b * C + c0) * spl;
-                __nv_bfloat16* ob = NHWC ? out + ((long long)b * hw + qofs) * C + c0 : out + ((long long)b * C + c0) * hw + qofs;
-                for (int c = lane; c < CN; c += 32) {
-                    const __nv_bfloat16* s = sb + c * sc;
-                    float acc = 0.f;
-#pragma unroll
-                    for (int i = 0; i < K; ++i)
-#pragma unroll
-                        for (int j = 0; j < K; ++j) {
-                            float v = 0.f;
-                            v += tx[j].wlo * ty[i].wlo * __bfloat162float(s[(ty[i].lo * Ws + tx[j].lo) * sp]);
-                            v += tx[j].whi * ty[i].wlo * __bfloat162float(s[(ty[i].lo * Ws + tx[j].hi) * sp]);
-                            v += tx[j].wlo * ty[i].whi * __bfloat162float(s[(ty[i].hi * Ws + tx[j].lo) * sp]);
-                            v += tx[j].whi * ty[i].whi * __bfloat162float(s[(ty[i].hi * Ws + tx[j].hi) * sp]);
-                            acc += p[i * K + j] * v;
-                        }
-                    acc *= 1.0f / static_cast<float>(KK);
-                    if (prev != nullptr) {
-                        const float qm = __bfloat162float(mask[(long long)b * hw + qofs]);
-                        const __nv_bfloat16* pb = NHWC ? prev + ((long long)b * hw + qofs) * C + c0 : prev + ((long long)b * C + c0) * hw + qofs;
-                        acc = __bfloat162float(pb[NHWC ? (long long)c : (long long)c * hw]) * (1.f - qm) + acc * qm;
-                    }
-                    ob[NHWC ? (long long)c : (long long)c * hw] = __float2bfloat16_rn(acc);
-                }
+                irregular_pixel<K, NHWC>(src, logits, out, prev, mask, b, C, c0, CN, Hs, Ws, H, W, qx, qy, qfx, qfy, lane);
             }
         }
     }
@@ -460,12 +424,21 @@ bool local_attn_fwd_tc_supported(int B, int C, int Hs, int Ws, int H, int W, int
     return layout == GFLA_NHWC ? aligned(out, 16) : (Ws % 8) == 0;
 }
 
+int local_attn_fwd_strip_tc(const void*, const void*, const void*, void*, void*, const void*, const void*, int, int, int, int,
+                            int, int, int, int, cudaStream_t);   // local_attn_strip_tc.cu
+
+// Channels-last inputs run the strip schedule (local_attn_strip_tc.cu).  GFLA_TC_STRIP: -1 = per-tile kernel of this
+// file instead, 0 = strip length chosen per launch, n > 0 = n tiles per strip.
+constexpr int kStripDefault = -1;
+
 int local_attn_fwd_tc(const void* src, const void* flow, const void* logits, void* out, void* probs, const void* prev,
                       const void* mask, int B, int C, int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype,
                       int layout, cudaStream_t st_) {
     if (!local_attn_fwd_tc_supported(B, C, Hs, Ws, H, W, k, dtype, flow_dtype, layout, src, out)) return GFLA_E_NOTSUP;
     const int cn = pick_cn(C);
     const bool nhwc = layout == GFLA_NHWC;
+    const int strip = tc::tune_knob("GFLA_TC_STRIP", kStripDefault);
+    if (nhwc && strip >= 0) return local_attn_fwd_strip_tc(src, flow, logits, out, probs, prev, mask, B, C, Hs, Ws, H, W, k, strip, st_);
 #define GFLA_TC_CASE(K_, CN_)                                                                                        \
     if (k == K_ && cn == CN_)                                                                                        \
         return nhwc ? tc::launch_tc<K_, CN_, true>(src, flow, logits, out, probs, prev, mask, B, C, Hs, Ws, H, W, st_)  \

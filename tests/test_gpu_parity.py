@@ -587,6 +587,24 @@ def test_tile_kernels_many_groups_small_grid(F_, oracle_lib):
     np.testing.assert_allclose(host(out), ref, rtol=0, atol=1e-2)
 
 
+@pytest.mark.parametrize("ts", [0, 1, 3, 16])
+@pytest.mark.parametrize("kind", ["smooth", "iid", "border"])
+def test_local_attn_strip_schedule_long_columns(F_, oracle_lib, monkeypatch, kind, ts):
+    """channels-last strip kernel: tall image (33 tile rows), more strips than SMs, every strip length incl. 1 (no row
+    sharing) and longer-than-the-image; the per-tile kernel (GFLA_TC_STRIP=-1) must give the same result to rounding"""
+    B, C, H, W, k = 4, 64, 264, 160, 5
+    s, f, l = _tile_inputs(B, C, H, W, H, W, k, kind, seed=11 + ts)
+    s = s.contiguous(memory_format=torch.channels_last)
+    monkeypatch.setenv("GFLA_TC_STRIP", str(ts))
+    out, probs = F_.local_attn_fwd(s, f, l, k, return_probs=True, algo="tile")
+    monkeypatch.setenv("GFLA_TC_STRIP", "-1")
+    per_tile = F_.local_attn_fwd(s, f, l, k, algo="tile")
+    assert (out.float() - per_tile.float()).abs().max().item() <= 2e-3      # same products, different summation order
+    ref, rprobs = oracle_lib.local_attn_fwd(host(s), f.cpu().numpy(), host(l), k, return_probs=True)
+    np.testing.assert_allclose(host(probs), rprobs, rtol=0, atol=4e-3)
+    np.testing.assert_allclose(host(out), ref, rtol=0, atol=1e-2)
+
+
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32, torch.float64])
 def test_relayout_roundtrip(F_, dt):
     torch.manual_seed(0)
