@@ -23,6 +23,7 @@ SIGNATURES = {
     "gfla_abi_version": [],
     "gfla_device_check": [],
     "gfla_debug_set_buffer": [_vp],
+    "gfla_debug_wait_profile": [_i, _i, _vp],
     "gfla_relayout": [_vp, _vp] + [_i] * 6 + [_vp],
     "gfla_block_extract_fwd": [_vp, _vp, _vp] + [_i] * 9 + [_vp],
     "gfla_block_extract_bwd": [_vp] * 5 + [_i] * 11 + [_vp],

@@ -20,6 +20,8 @@ int local_attn_fwd_tc(const void*, const void*, const void*, void*, void*, const
 int relayout(const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int tc_debug_set_buffer(void*);
 int tc_debug_set_buffer_bwd(void*);
+int tc_wait_profile_fwd(int, unsigned long long*);
+int tc_wait_profile_strip(int, unsigned long long*);
 bool local_attn_fwd_tc_supported(int B, int C, int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, int layout, const void* src, const void* out);
 }  // namespace gfla
 
@@ -54,6 +56,13 @@ int gfla_device_check(void) {
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
     cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
     return (major == 10 && minor == 0) ? GFLA_OK : static_cast<int>(cudaErrorNoKernelImageForDevice);
+}
+
+int gfla_debug_wait_profile(int which, int enable, unsigned long long* out_u64x32) {
+    if (which != 0 && which != 1) return GFLA_E_SHAPE;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return static_cast<int>(e);
+    return which == 0 ? tc_wait_profile_fwd(enable, out_u64x32) : tc_wait_profile_strip(enable, out_u64x32);
 }
 
 int gfla_debug_set_buffer(void* host_mapped_u64x8) {

@@ -87,6 +87,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_TMEM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t_start = clock64();
     StripGeom geo;
     geo.gxn = (W + GW - 1) / GW;
     geo.gyn = (H + GH - 1) / GH;
@@ -364,6 +365,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 2 * CN >= 32 ? 2 * CN : 32);
+    tc_profile_total(t_start);
 }
 
 template <int K, int CN>
@@ -397,6 +399,8 @@ static int launch_strip(const void* src, const void* flow, const void* logits, v
 }
 
 }  // namespace tc
+
+int tc_wait_profile_strip(int enable, unsigned long long* out32) { return tc::tc_wait_profile(enable, out32); }
 
 // channels-last only; same eligibility as local_attn_fwd_tc (checked by the caller).  ts = tiles per strip, 0 = automatic.
 int local_attn_fwd_strip_tc(const void* src, const void* flow, const void* logits, void* out, void* probs, const void* prev,

@@ -99,6 +99,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_TMEM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t_start = clock64();
     const int gxn = (W + GW - 1) / GW, gyn = (H + GH - 1) / GH;
     const int ngroups = B * gyn * gxn;
     const int c0 = blockIdx.y * CN;
@@ -133,7 +134,9 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             // rows yet, so pull them into L2 now -- a whole group of time before the TMA loads need them
             const int gn = g + gridDim.x;
             if (gn < ngroups) {
+                const long long tb0 = clock64();
                 bbox_of(gn, nx0, ny0, nx1, ny1);
+                tc_profile_add(0, 6, clock64() - tb0);      // next group's bounding box
                 const int bn = gn / (gxn * gyn), prow = ny1 - ny0 + 1;
                 if ((knobs & 255) == 2 && NHWC && CN == C) {
                     // channels-last, all channels in this CTA: a row segment of the box is one contiguous range
@@ -236,6 +239,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             const bool valid = px < W && py < H;
             int X0 = 0, Y0 = 0;
             bool live = false;
+            const long long tw0 = clock64();
             if (valid && !(knobs & 512)) {   // bit 9: timing experiment, skip the per-pixel window construction
                 const long long pofs = (long long)py * W + px;
                 float p[KK];
@@ -254,14 +258,17 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                     store_window_words<K>(wsm_a, w);
                 }
             }
+            tc_profile_add(2, 6, clock64() - tw0);          // window construction
             mbar_wait(&info_full[gi % NINFO], (gi / NINFO) & 1, 0x020500, gi);
             const GroupInfo inf = infos[gi % NINFO];
+            long long fill_cycles = 0;
             for (int cb = 0; cb < inf.ncb; ++cb) {
                 const int e0 = X0 - (inf.x0 + cb * FBW);           // box position of window column 0
                 const bool cols_hit = live && e0 > -K1 && e0 < FBW && !(knobs & 1024);   // bit 10: timing experiment
                 for (int rc = 0; rc < inf.nrc; ++rc, ++it) {
                     const int slot = it % NSTAGE;
                     mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x020200 | slot, it);
+                    const long long tf0 = clock64();
                     const uint32_t a_stage = a_base + slot * SM::A_STAGE;
                     const int R0 = inf.y0 + rc * RCH;
                     bool wrote = false;
@@ -271,8 +278,10 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                                                   1u << (slot * RCH + rr));
                     if (wrote) fence_proxy_async_smem();
                     mbar_arrive(&full_a[slot]);
+                    fill_cycles += clock64() - tf0;
                 }
             }
+            tc_profile_add(2, 7, fill_cycles);              // slab fills
         }
     } else {
         // ================================================================= epilogue
@@ -294,6 +303,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             const int buf = gi & 1;
             mbar_wait(&acc_full[buf], (gi >> 1) & 1, 0x030300 | buf, gi);
             tc_fence_after();
+            const long long te0 = clock64();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * CN;
             __nv_bfloat16* o = NHWC ? out + ((long long)b * hw + pofs) * C + c0 : out + ((long long)b * C + c0) * hw + pofs;
             // optional fused mask blend (generator.py:130): out = prev * (1 - mask) + attention * mask
@@ -348,6 +358,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            tc_profile_add(3, 6, clock64() - te0);          // TMEM -> registers -> global
             // irregular pixels keep the reference's literal 4-tap arithmetic; the warp shares each one (tile_window.cuh)
             unsigned todo = __ballot_sync(0xffffffffu, valid && !regular);
             while (todo) {
@@ -362,6 +373,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 2 * CN >= 32 ? 2 * CN : 32);
+    tc_profile_total(t_start);
 }
 
 template <int K, int CN, bool NHWC>
@@ -402,6 +414,8 @@ static int launch_tc(const void* src, const void* flow, const void* logits, void
 }
 
 }  // namespace tc
+
+int tc_wait_profile_fwd(int enable, unsigned long long* out32) { return tc::tc_wait_profile(enable, out32); }
 
 int tc_debug_set_buffer(void* host_mapped) {
     unsigned long long* p = static_cast<unsigned long long*>(host_mapped);

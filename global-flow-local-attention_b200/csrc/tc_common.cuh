@@ -48,12 +48,37 @@ static __device__ __noinline__ void mbar_timeout(uint32_t tag, uint32_t parity, 
     }
     __trap();
 }
+// Wait profile (debug, off by default): cycles that lane 0 of every warp spent blocked, per (role, barrier kind) of
+// the tag; slot 7 of role 0 = total kernel cycles summed over the CTAs.  Read through gfla_debug_wait_profile().
+static __device__ unsigned long long g_tc_prof[32];
+static __device__ int g_tc_prof_on = 0;
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0, uint32_t iter = 0) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 2000000000LL) mbar_timeout(tag, parity, iter);  // ~1 s
     }
+    if (g_tc_prof_on && (threadIdx.x & 31) == 0)
+        atomicAdd(&g_tc_prof[((tag >> 16) & 3) * 8 + ((tag >> 8) & 7)], static_cast<unsigned long long>(clock64() - t0));
+}
+// host side of the wait profile for the translation unit that includes this header
+inline int tc_wait_profile(int enable, unsigned long long* out32) {
+    cudaError_t e = cudaSuccess;
+    if (out32 != nullptr) e = cudaMemcpyFromSymbol(out32, g_tc_prof, sizeof(unsigned long long) * 32);
+    if (e == cudaSuccess) {
+        const unsigned long long zero[32] = {};
+        e = cudaMemcpyToSymbol(g_tc_prof, zero, sizeof(zero));
+    }
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_tc_prof_on, &enable, sizeof(int));
+    return static_cast<int>(e);
+}
+// explicit region timers for the same profile (kinds 6, 7 of a role): call from lane 0 of a warp
+__device__ __forceinline__ void tc_profile_add(int role, int kind, long long cycles) {
+    if (g_tc_prof_on && (threadIdx.x & 31) == 0) atomicAdd(&g_tc_prof[role * 8 + kind], static_cast<unsigned long long>(cycles));
+}
+__device__ __forceinline__ void tc_profile_total(long long t_start) {
+    if (g_tc_prof_on && threadIdx.x == 0) atomicAdd(&g_tc_prof[7], static_cast<unsigned long long>(clock64() - t_start));
 }
 
 // explicit shared-space accesses (32-bit shared addresses): keeps ptxas from falling back to generic LD/ST
