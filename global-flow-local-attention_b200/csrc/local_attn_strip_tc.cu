@@ -64,6 +64,29 @@ struct StripGeom {
     }
 };
 
+// the tiles of one CTA in processing order: strips blockIdx.x, blockIdx.x + gridDim.x, ..., top to bottom inside a strip
+struct TileIt {
+    int unit, b, gx, ty, ty1;
+    __device__ __forceinline__ bool ok(const StripGeom& g) const { return unit < g.units; }
+    __device__ __forceinline__ void enter(const StripGeom& g) {
+        if (unit < g.units) {
+            int ty0;
+            g.decode(unit, b, gx, ty0, ty1);
+            ty = ty0;
+        }
+    }
+    __device__ __forceinline__ void start(const StripGeom& g, int first_unit) {
+        unit = first_unit; b = 0; gx = 0; ty = 0; ty1 = 0;
+        enter(g);
+    }
+    __device__ __forceinline__ void next(const StripGeom& g, int stride) {
+        if (++ty >= ty1) {
+            unit += stride;
+            enter(g);
+        }
+    }
+};
+
 template <int K, int CN>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfloat16* __restrict__ src,
@@ -110,109 +133,140 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    TileIt first;
+    first.start(geo, blockIdx.x);
+    const int ustride = gridDim.x;
+
     if (warp == 0) {
         // ================================================================= producer
+        // The flow of a tile is loaded a whole pass before its bounding box is needed (TileFlow registers in flight
+        // across the TMA loop): a box costs ~4 us of load latency, which otherwise stalls the row loads once per tile.
+        TileIt cur = first, ld = first, pend_it = first;
+        TileFlow fr;
+        TileBox box0 = TileBox{0, 0, 0, 0}, box1 = box0;
+        int unit1 = -1;
+        bool pend = false;
+        if (ld.ok(geo)) {
+            tile_flow_load(flow, ld.b, ld.gx * GW, ld.ty * GH, H, W, lane, fr);
+            tile_bbox_reduce<K>(fr, ld.gx * GW, ld.ty * GH, H, W, Hs, Ws, lane, false, box0.x0, box0.y0, box0.x1, box0.y1);
+            ld.next(geo, ustride);
+        }
+        if (ld.ok(geo)) {
+            tile_flow_load(flow, ld.b, ld.gx * GW, ld.ty * GH, H, W, lane, fr);
+            tile_bbox_reduce<K>(fr, ld.gx * GW, ld.ty * GH, H, W, Hs, Ws, lane, false, box1.x0, box1.y0, box1.x1, box1.y1);
+            unit1 = ld.unit;
+            ld.next(geo, ustride);
+        }
+        if (ld.ok(geo)) {
+            tile_flow_load(flow, ld.b, ld.gx * GW, ld.ty * GH, H, W, lane, fr);
+            pend_it = ld;
+            pend = true;
+            ld.next(geo, ustride);
+        }
         uint32_t it = 0;  // global step counter
         int ti = 0;       // global tile counter of this CTA
-        for (int unit = blockIdx.x; unit < geo.units; unit += gridDim.x) {
-            int b, gx, ty0, ty1;
-            geo.decode(unit, b, gx, ty0, ty1);
-            TileBox cur, nxt = TileBox{0, 0, 0, 0};
-            group_bbox<K>(flow, b, gx * GW, ty0 * GH, H, W, Hs, Ws, lane, false, cur.x0, cur.y0, cur.x1, cur.y1);
-            int k0 = 1, k1 = 0;
-            for (int ty = ty0; ty < ty1; ++ty, ++ti) {
-                const bool has_next = ty + 1 < ty1;
-                if (has_next) group_bbox<K>(flow, b, gx * GW, (ty + 1) * GH, H, W, Hs, Ws, lane, false, nxt.x0, nxt.y0, nxt.x1, nxt.y1);
-                const StripTile t = strip_plan(cur, has_next, nxt, k0, k1, FBW);
-                if (lane == 0) {
-                    infos[ti % ST_NINFO] = t;
-                    mbar_arrive(&info_full[ti % ST_NINFO]);
-                }
-                for (int cb = 0; cb < t.ncb; ++cb)
-                    for (int j = t.j0; j <= t.j1; ++j) {
-                        if (strip_skipped(t, j)) continue;
-                        const int slot = it % NSTAGE;
-                        mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x000200 | slot, it);
-                        if (lane == 0) {
-                            mbar_arrive_expect_tx(&full_s[slot], SM::S_STAGE);
-#pragma unroll
-                            for (int rr = 0; rr < RCH; ++rr) {
-                                uint8_t* dst = smem + SM::OFF_S + slot * SM::S_STAGE + rr * SM::S_SLAB;
-#pragma unroll
-                                for (int cg = 0; cg < CN / 64; ++cg)   // [CN/64 channel groups][FBW x][64 channels]
-                                    tma_load_4d(dst + cg * (FBW * 128), &tmap_src, &full_s[slot], c0 + cg * 64, t.xs + cb * FBW,
-                                                2 * j + rr, b);
-                            }
-                        }
-                        __syncwarp();
-                        ++it;
-                    }
-                k0 = t.s0; k1 = t.s1;
-                cur = nxt;
+        int k0 = 1, k1 = 0;
+        for (; cur.ok(geo); cur.next(geo, ustride), ++ti) {
+            const bool has_next = unit1 == cur.unit;   // the next tile of this CTA continues the same strip
+            const StripTile t = strip_plan(box0, has_next, box1, k0, k1, FBW);
+            if (lane == 0) {
+                infos[ti % ST_NINFO] = t;
+                mbar_arrive(&info_full[ti % ST_NINFO]);
             }
+            for (int cb = 0; cb < t.ncb; ++cb)
+                for (int j = t.j0; j <= t.j1; ++j) {
+                    if (strip_skipped(t, j)) continue;
+                    const int slot = it % NSTAGE;
+                    mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x000200 | slot, it);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&full_s[slot], SM::S_STAGE);
+#pragma unroll
+                        for (int rr = 0; rr < RCH; ++rr) {
+                            uint8_t* dst = smem + SM::OFF_S + slot * SM::S_STAGE + rr * SM::S_SLAB;
+#pragma unroll
+                            for (int cg = 0; cg < CN / 64; ++cg)   // [CN/64 channel groups][FBW x][64 channels]
+                                tma_load_4d(dst + cg * (FBW * 128), &tmap_src, &full_s[slot], c0 + cg * 64, t.xs + cb * FBW,
+                                            2 * j + rr, cur.b);
+                        }
+                    }
+                    __syncwarp();
+                    ++it;
+                }
+            k0 = t.s0; k1 = t.s1;
+            const long long tb0 = clock64();
+            box0 = box1;
+            if (pend) {
+                tile_bbox_reduce<K>(fr, pend_it.gx * GW, pend_it.ty * GH, H, W, Hs, Ws, lane, false, box1.x0, box1.y0, box1.x1, box1.y1);
+                unit1 = pend_it.unit;
+            } else {
+                unit1 = -1;
+            }
+            pend = ld.ok(geo);
+            if (pend) {
+                tile_flow_load(flow, ld.b, ld.gx * GW, ld.ty * GH, H, W, lane, fr);
+                pend_it = ld;
+                ld.next(geo, ustride);
+            }
+            tc_profile_add(0, 6, clock64() - tb0);          // box of tile n+2, flow loads of tile n+3
         }
     } else if (warp == 1) {
         // ================================================================= MMA issuer
         constexpr uint32_t idesc = make_idesc_f16(128, CN, true, false, true);
         uint32_t it = 0;
         int ti = 0;
-        for (int unit = blockIdx.x; unit < geo.units; unit += gridDim.x) {
-            int b, gx, ty0, ty1;
-            geo.decode(unit, b, gx, ty0, ty1);
-            bool started = false;   // this tile's accumulator already holds the previous pass's shared steps
-            for (int ty = ty0; ty < ty1; ++ty, ++ti) {
-                mbar_wait(&info_full[ti % ST_NINFO], (ti / ST_NINFO) & 1, 0x010500, ti);
-                const StripTile t = infos[ti % ST_NINFO];
-                const int buf = ti & 1;
-                bool next_started = false;
-                for (int cb = 0; cb < t.ncb; ++cb)
-                    for (int j = t.j0; j <= t.j1; ++j) {
-                        if (strip_skipped(t, j)) continue;
-                        const bool shared = strip_shared(t, j);
-                        if (!started) {   // first touch of this tile's TMEM half: its previous user must be drained
-                            mbar_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1, 0x010400 | buf, ti);
-                            tc_fence_after();
-                        }
-                        if (shared && !next_started) {
-                            mbar_wait(&acc_empty[buf ^ 1], (((ti + 1) >> 1) & 1) ^ 1, 0x010600 | (buf ^ 1), ti);
-                            tc_fence_after();
-                        }
-                        const int slot = it % NSTAGE;
-                        const uint32_t par = (it / NSTAGE) & 1;
-                        mbar_wait(&full_s[slot], par, 0x010000 | slot, it);
-                        mbar_wait(&full_a[slot], par, 0x010100 | slot, it);
+        bool started = false;   // this tile's accumulator already holds the previous pass's shared steps
+        for (TileIt cur = first; cur.ok(geo); cur.next(geo, ustride), ++ti) {
+            mbar_wait(&info_full[ti % ST_NINFO], (ti / ST_NINFO) & 1, 0x010500, ti);
+            const StripTile t = infos[ti % ST_NINFO];
+            const int buf = ti & 1;
+            bool next_started = false;
+            for (int cb = 0; cb < t.ncb; ++cb)
+                for (int j = t.j0; j <= t.j1; ++j) {
+                    if (strip_skipped(t, j)) continue;
+                    const bool shared = strip_shared(t, j);
+                    if (!started) {   // first touch of this tile's TMEM half: its previous user must be drained
+                        mbar_wait(&acc_empty[buf], ((ti >> 1) & 1) ^ 1, 0x010400 | buf, ti);
                         tc_fence_after();
-                        if (lane == 0) {
-                            const uint32_t a0 = smem_u32(smem + SM::OFF_A + slot * SM::A_STAGE);
-                            const uint32_t b0 = smem_u32(smem + SM::OFF_S + slot * SM::S_STAGE);
-#pragma unroll
-                            for (int sub = 0; sub < 2; ++sub) {
-                                if (sub == 1 && !shared) break;
-                                const uint32_t d_tmem = tmem_base + (sub == 0 ? buf : (buf ^ 1)) * CN;
-                                const bool fresh = sub == 0 ? !started : !next_started;
-#pragma unroll
-                                for (int rr = 0; rr < RCH; ++rr)
-#pragma unroll
-                                    for (int h = 0; h < FBW / 16; ++h) {  // K = 16 positions per MMA
-                                        // A = [128 px][32 pos], K-major, 64B rows, 64B swizzle; K-advance = +32 B
-                                        const uint64_t ad = make_smem_desc(a0 + sub * SM::A_TILE + rr * SM::FA_SLAB + h * 32, 16, 512, kSwizzle64);
-                                        // B = [32 x][64 ch] per channel group, MN-major, 128B swizzle: LBO = next channel group,
-                                        // SBO = next 8 positions (1 KB); K-advance = 2 KB
-                                        const uint64_t bd = make_smem_desc(b0 + rr * SM::S_SLAB + h * 2048, FBW * 128, 1024, kSwizzle128);
-                                        umma_f16(d_tmem, ad, bd, idesc, (fresh && rr == 0 && h == 0) ? 0u : 1u);
-                                    }
-                            }
-                            tc_commit(&empty[slot]);
-                        }
-                        __syncwarp();
-                        started = true;
-                        if (shared) next_started = true;
-                        ++it;
                     }
-                if (lane == 0) tc_commit(&acc_full[buf]);
-                __syncwarp();
-                started = next_started;
-            }
+                    if (shared && !next_started) {
+                        mbar_wait(&acc_empty[buf ^ 1], (((ti + 1) >> 1) & 1) ^ 1, 0x010600 | (buf ^ 1), ti);
+                        tc_fence_after();
+                    }
+                    const int slot = it % NSTAGE;
+                    const uint32_t par = (it / NSTAGE) & 1;
+                    mbar_wait(&full_s[slot], par, 0x010000 | slot, it);
+                    mbar_wait(&full_a[slot], par, 0x010100 | slot, it);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a0 = smem_u32(smem + SM::OFF_A + slot * SM::A_STAGE);
+                        const uint32_t b0 = smem_u32(smem + SM::OFF_S + slot * SM::S_STAGE);
+#pragma unroll
+                        for (int sub = 0; sub < 2; ++sub) {
+                            if (sub == 1 && !shared) break;
+                            const uint32_t d_tmem = tmem_base + (sub == 0 ? buf : (buf ^ 1)) * CN;
+                            const bool fresh = sub == 0 ? !started : !next_started;
+#pragma unroll
+                            for (int rr = 0; rr < RCH; ++rr)
+#pragma unroll
+                                for (int h = 0; h < FBW / 16; ++h) {  // K = 16 positions per MMA
+                                    // A = [128 px][32 pos], K-major, 64B rows, 64B swizzle; K-advance = +32 B
+                                    const uint64_t ad = make_smem_desc(a0 + sub * SM::A_TILE + rr * SM::FA_SLAB + h * 32, 16, 512, kSwizzle64);
+                                    // B = [32 x][64 ch] per channel group, MN-major, 128B swizzle: LBO = next channel group,
+                                    // SBO = next 8 positions (1 KB); K-advance = 2 KB
+                                    const uint64_t bd = make_smem_desc(b0 + rr * SM::S_SLAB + h * 2048, FBW * 128, 1024, kSwizzle128);
+                                    umma_f16(d_tmem, ad, bd, idesc, (fresh && rr == 0 && h == 0) ? 0u : 1u);
+                                }
+                        }
+                        tc_commit(&empty[slot]);
+                    }
+                    __syncwarp();
+                    started = true;
+                    if (shared) next_started = true;
+                    ++it;
+                }
+            if (lane == 0) tc_commit(&acc_full[buf]);
+            __syncwarp();
+            started = next_started;   // false after the last tile of a strip (it never shares)
         }
     } else if (warp < 6) {
         // ================================================================= builders
@@ -223,76 +277,110 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
         const uint32_t swz = ((m >> 1) & 3) << 4;                               // 64B-swizzle XOR of this row's 16B chunks
         uint32_t it = 0, dirty = 0xffffffffu;   // slab rows start with unknown contents: treat them as dirty
         int ti = 0;
-        // collapsed window of pixel m of tile (b, gx, ty) -> shared memory; returns whether the pixel is regular
-        auto make_window = [&](int b, int gx, int ty, uint32_t wsm_a, int& X0, int& Y0) -> bool {
-            const int px = gx * GW + (m & 15), py = ty * GH + (m >> 4);
+        // Raw inputs of this thread's pixel of one tile.  Like the producer's flow, they are loaded one pass before the
+        // window is built from them, so their latency hides behind the slab fills of the current tile.
+        __nv_bfloat16 lg[KK];
+        float pfx = 0.f, pfy = 0.f;
+        auto load_pixel = [&](const TileIt& tl) {
+            const int px = tl.gx * GW + (m & 15), py = tl.ty * GH + (m >> 4);
+            if (px < W && py < H) {
+                const long long pofs = (long long)py * W + px;
+                const __nv_bfloat16* lp = logits + (long long)tl.b * KK * hw + pofs;
+#pragma unroll
+                for (int t = 0; t < KK; ++t) lg[t] = lp[t * hw];
+                pfx = flow[(long long)tl.b * 2 * hw + pofs];
+                pfy = flow[(long long)tl.b * 2 * hw + hw + pofs];
+            }
+        };
+        // collapsed window of that pixel -> shared memory; returns whether the pixel exists and is regular
+        auto make_window = [&](const TileIt& tl, uint32_t wsm_a, int& X0, int& Y0) -> bool {
+            const int px = tl.gx * GW + (m & 15), py = tl.ty * GH + (m >> 4);
             X0 = 0; Y0 = 0;
             if (!(px < W && py < H)) return false;
             const long long pofs = (long long)py * W + px;
             float p[KK];
-            pixel_softmax_f32<KK>(logits + (long long)b * KK * hw + pofs, hw, p);
+#pragma unroll
+            for (int t = 0; t < KK; ++t) p[t] = __bfloat162float(lg[t]);
+            softmax_inplace_f32<KK>(p);
             if (probs != nullptr && blockIdx.y == 0) {
-                __nv_bfloat16* pr = probs + (long long)b * KK * hw + pofs;
+                __nv_bfloat16* pr = probs + (long long)tl.b * KK * hw + pofs;
 #pragma unroll
                 for (int t = 0; t < KK; ++t) pr[t * hw] = __float2bfloat16_rn(p[t]);
             }
-            const float fx = flow[(long long)b * 2 * hw + pofs], fy = flow[(long long)b * 2 * hw + hw + pofs];
             AxisTap<float> tx[K], ty_[K];
-            if (!taps_regular<K>(fx, fy, px, py, Hs, Ws, tx, ty_)) return false;
+            if (!taps_regular<K>(pfx, pfy, px, py, Hs, Ws, tx, ty_)) return false;
             float w[K1 * K1];
             build_window<K>(p, tx, ty_, Hs, Ws, inv_kk, w, X0, Y0);
             store_window_words<K>(wsm_a, w);
             return true;
         };
-        for (int unit = blockIdx.x; unit < geo.units; unit += gridDim.x) {
-            int b, gx, ty0, ty1;
-            geo.decode(unit, b, gx, ty0, ty1);
-            int X0 = 0, Y0 = 0, nX0 = 0, nY0 = 0;
-            bool live = false, nlive = false, have = false;   // have: this tile's window was built during the previous pass
-            for (int ty = ty0; ty < ty1; ++ty, ++ti) {
-                const uint32_t wsm_cur = wsm_base + (ti & 1) * SM::W_TILE, wsm_nxt = wsm_base + ((ti + 1) & 1) * SM::W_TILE;
-                if (have) { X0 = nX0; Y0 = nY0; live = nlive; }
-                else live = make_window(b, gx, ty, wsm_cur, X0, Y0);
-                mbar_wait(&info_full[ti % ST_NINFO], (ti / ST_NINFO) & 1, 0x020500, ti);
-                const StripTile t = infos[ti % ST_NINFO];
-                have = t.s0 <= t.s1;
-                if (have) nlive = make_window(b, gx, ty + 1, wsm_nxt, nX0, nY0);
-                for (int cb = 0; cb < t.ncb; ++cb) {
-                    const int e0 = X0 - (t.xs + cb * FBW), e0n = nX0 - (t.xs + cb * FBW);   // box position of window column 0
-                    const bool cols_hit = live && e0 > -K1 && e0 < FBW;
-                    const bool cols_hit_n = have && nlive && e0n > -K1 && e0n < FBW;
-                    for (int j = t.j0; j <= t.j1; ++j) {
-                        if (strip_skipped(t, j)) continue;
-                        const int slot = it % NSTAGE;
-                        mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x020200 | slot, it);
-                        const uint32_t a_stage = a_base + slot * SM::A_STAGE;
-                        const int R0 = 2 * j;
-                        bool wrote = false;
+        TileIt ld = first, pend_it = first;
+        int X0 = 0, Y0 = 0, nX0 = 0, nY0 = 0;
+        bool live = false, nlive = false, pend = false;
+        if (ld.ok(geo)) {
+            load_pixel(ld);
+            live = make_window(ld, wsm_base, X0, Y0);
+            ld.next(geo, ustride);
+        }
+        if (ld.ok(geo)) {
+            load_pixel(ld);
+            pend_it = ld;
+            pend = true;
+            ld.next(geo, ustride);
+        }
+        for (TileIt cur = first; cur.ok(geo); cur.next(geo, ustride), ++ti) {
+            const uint32_t wsm_cur = wsm_base + (ti & 1) * SM::W_TILE, wsm_nxt = wsm_base + ((ti + 1) & 1) * SM::W_TILE;
+            const long long tw0 = clock64();
+            const bool have_n = pend;             // this CTA's next tile (same strip or not): its window is built now
+            if (pend) nlive = make_window(pend_it, wsm_nxt, nX0, nY0);
+            pend = ld.ok(geo);
+            if (pend) {
+                load_pixel(ld);
+                pend_it = ld;
+                ld.next(geo, ustride);
+            }
+            tc_profile_add(2, 6, clock64() - tw0);          // window of tile n+1, loads of tile n+2
+            mbar_wait(&info_full[ti % ST_NINFO], (ti / ST_NINFO) & 1, 0x020500, ti);
+            const StripTile t = infos[ti % ST_NINFO];
+            long long fill_cycles = 0;
+            for (int cb = 0; cb < t.ncb; ++cb) {
+                const int e0 = X0 - (t.xs + cb * FBW), e0n = nX0 - (t.xs + cb * FBW);   // box position of window column 0
+                const bool cols_hit = live && e0 > -K1 && e0 < FBW;
+                const bool cols_hit_n = have_n && nlive && e0n > -K1 && e0n < FBW;
+                for (int j = t.j0; j <= t.j1; ++j) {
+                    if (strip_skipped(t, j)) continue;
+                    const int slot = it % NSTAGE;
+                    mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x020200 | slot, it);
+                    const long long tf0 = clock64();
+                    const uint32_t a_stage = a_base + slot * SM::A_STAGE;
+                    const int R0 = 2 * j;
+                    bool wrote = false;
+#pragma unroll
+                    for (int rr = 0; rr < RCH; ++rr)
+                        wrote |= fill_slab_row<K, FBW>(a_stage + rr * SM::FA_SLAB, swz, wsm_cur, cols_hit, (R0 + rr) - Y0, e0, dirty,
+                                                  1u << ((slot * RCH + rr) * 2));
+                    if (strip_shared(t, j)) {   // only inside a strip: the next tile is the one whose window was just built
 #pragma unroll
                         for (int rr = 0; rr < RCH; ++rr)
-                            wrote |= fill_slab_row<K, FBW>(a_stage + rr * SM::FA_SLAB, swz, wsm_cur, cols_hit, (R0 + rr) - Y0, e0, dirty,
-                                                      1u << ((slot * RCH + rr) * 2));
-                        if (strip_shared(t, j)) {
-#pragma unroll
-                            for (int rr = 0; rr < RCH; ++rr)
-                                wrote |= fill_slab_row<K, FBW>(a_stage + SM::A_TILE + rr * SM::FA_SLAB, swz, wsm_nxt, cols_hit_n,
-                                                          (R0 + rr) - nY0, e0n, dirty, 1u << ((slot * RCH + rr) * 2 + 1));
-                        }
-                        if (wrote) fence_proxy_async_smem();
-                        mbar_arrive(&full_a[slot]);
-                        ++it;
+                            wrote |= fill_slab_row<K, FBW>(a_stage + SM::A_TILE + rr * SM::FA_SLAB, swz, wsm_nxt, cols_hit_n,
+                                                      (R0 + rr) - nY0, e0n, dirty, 1u << ((slot * RCH + rr) * 2 + 1));
                     }
+                    if (wrote) fence_proxy_async_smem();
+                    mbar_arrive(&full_a[slot]);
+                    fill_cycles += clock64() - tf0;
+                    ++it;
                 }
             }
+            tc_profile_add(2, 7, fill_cycles);              // slab fills
+            X0 = nX0; Y0 = nY0; live = nlive;
         }
     } else {
         // ================================================================= epilogue
         const int q = warp & 3, m = q * 32 + lane;
         int ti = 0;
-        for (int unit = blockIdx.x; unit < geo.units; unit += gridDim.x) {
-            int b, gx, ty0, ty1;
-            geo.decode(unit, b, gx, ty0, ty1);
-            for (int ty = ty0; ty < ty1; ++ty, ++ti) {
+        {
+            for (TileIt cur = first; cur.ok(geo); cur.next(geo, ustride), ++ti) {
+                const int b = cur.b, gx = cur.gx, ty = cur.ty;
                 const int px = gx * GW + (m & 15), py = ty * GH + (m >> 4);
                 const bool valid = px < W && py < H;
                 const long long pofs = (long long)py * W + px;
@@ -307,6 +395,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
                 const int buf = ti & 1;
                 mbar_wait(&acc_full[buf], (ti >> 1) & 1, 0x030300 | buf, ti);
                 tc_fence_after();
+                const long long te0 = clock64();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * CN;
                 __nv_bfloat16* o = out + ((long long)b * hw + pofs) * C + c0;
                 // optional fused mask blend (generator.py:130): out = prev * (1 - mask) + attention * mask
@@ -349,6 +438,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                tc_profile_add(3, 6, clock64() - te0);          // TMEM -> registers -> global
                 // irregular pixels (fp32 rounding of (flow+offset)+coord straddling an integer, ~1e-5 of all pixels): the
                 // reference's literal 4-taps-per-(i,j) arithmetic, the warp shares one pixel (lanes split the channels)
                 unsigned todo = __ballot_sync(0xffffffffu, valid && !regular);

@@ -54,13 +54,13 @@ static __device__ unsigned long long g_tc_prof[32];
 static __device__ int g_tc_prof_on = 0;
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0, uint32_t iter = 0) {
-    if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    while (!mbar_try_wait(bar, parity)) {   // try_wait itself suspends the thread for a while before giving up
         if (clock64() - t0 > 2000000000LL) mbar_timeout(tag, parity, iter);  // ~1 s
     }
-    if (g_tc_prof_on && (threadIdx.x & 31) == 0)
-        atomicAdd(&g_tc_prof[((tag >> 16) & 3) * 8 + ((tag >> 8) & 7)], static_cast<unsigned long long>(clock64() - t0));
+    const long long dt = clock64() - t0;
+    if (dt > 64 && g_tc_prof_on && (threadIdx.x & 31) == 0)
+        atomicAdd(&g_tc_prof[((tag >> 16) & 3) * 8 + ((tag >> 8) & 7)], static_cast<unsigned long long>(dt));
 }
 // host side of the wait profile for the translation unit that includes this header
 inline int tc_wait_profile(int enable, unsigned long long* out32) {

@@ -37,6 +37,23 @@ __device__ __forceinline__ void pixel_softmax_f32(const __nv_bfloat16* __restric
     for (int t = 0; t < KK; ++t) p[t] *= inv;
 }
 
+// the same from logits already held in registers (p[t] = logit on entry)
+template <int KK>
+__device__ __forceinline__ void softmax_inplace_f32(float* p) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < KK; ++t) mx = fmaxf(mx, p[t]);
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < KK; ++t) {
+        p[t] = expf(p[t] - mx);
+        sum += p[t];
+    }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int t = 0; t < KK; ++t) p[t] *= inv;
+}
+
 // the k taps per axis, evaluated exactly like the reference; "regular" = consecutive integers
 template <int K>
 __device__ __forceinline__ bool taps_regular(float flow_x, float flow_y, int x, int y, int Hs, int Ws,
@@ -51,23 +68,37 @@ __device__ __forceinline__ bool taps_regular(float flow_x, float flow_y, int x, 
     return regular;
 }
 
-// bounding box (clamped tap positions) of one 16x8 pixel group: warp-collective.
+// Flow of this lane's 4 pixels of a 16x8 pixel group (pixel m = lane + 32 i; zeros outside the image).  Split from
+// the reduction below so that a producer can issue the loads a whole tile of work before it needs the box.
+struct TileFlow { float fx[4], fy[4]; };
+
+__device__ __forceinline__ void tile_flow_load(const float* __restrict__ flow, int b, int gx0, int gy0, int H, int W, int lane,
+                                               TileFlow& r) {
+    const long long hw = (long long)H * W;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = lane + 32 * i, px = gx0 + (m & 15), py = gy0 + (m >> 4);
+        const bool valid = px < W && py < H;
+        const long long o = (long long)b * 2 * hw + (long long)py * W + px;
+        r.fx[i] = valid ? flow[o] : 0.f;
+        r.fy[i] = valid ? flow[o + hw] : 0.f;
+    }
+}
+
+// bounding box (clamped tap positions) of one 16x8 pixel group from its flow values: warp-collective.
 // align_x8: NCHW tensor maps need the innermost (x) box origin on a 16-byte boundary.
 template <int K>
-__device__ __forceinline__ void group_bbox(const float* __restrict__ flow, int b, int gx0, int gy0, int H, int W, int Hs,
-                                           int Ws, int lane, bool align_x8, int& x0, int& y0, int& x1, int& y1) {
-    const long long hw = (long long)H * W;
+__device__ __forceinline__ void tile_bbox_reduce(const TileFlow& r, int gx0, int gy0, int H, int W, int Hs, int Ws, int lane,
+                                                 bool align_x8, int& x0, int& y0, int& x1, int& y1) {
     int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int m = lane + 32 * i, px = gx0 + (m & 15), py = gy0 + (m >> 4);
         if (px < W && py < H) {
-            const long long o = (long long)b * 2 * hw + (long long)py * W + px;
-            const float fx = flow[o], fy = flow[o + hw];
-            xmin = min(xmin, axis_tap<float>(fx, -(K / 2), px, Ws).lo);
-            xmax = max(xmax, axis_tap<float>(fx, K - 1 - K / 2, px, Ws).hi);
-            ymin = min(ymin, axis_tap<float>(fy, -(K / 2), py, Hs).lo);
-            ymax = max(ymax, axis_tap<float>(fy, K - 1 - K / 2, py, Hs).hi);
+            xmin = min(xmin, axis_tap<float>(r.fx[i], -(K / 2), px, Ws).lo);
+            xmax = max(xmax, axis_tap<float>(r.fx[i], K - 1 - K / 2, px, Ws).hi);
+            ymin = min(ymin, axis_tap<float>(r.fy[i], -(K / 2), py, Hs).lo);
+            ymax = max(ymax, axis_tap<float>(r.fy[i], K - 1 - K / 2, py, Hs).hi);
         }
     }
 #pragma unroll
@@ -79,6 +110,14 @@ __device__ __forceinline__ void group_bbox(const float* __restrict__ flow, int b
     }
     if (align_x8) xmin &= ~7;
     x0 = xmin; y0 = ymin; x1 = xmax; y1 = ymax;
+}
+
+template <int K>
+__device__ __forceinline__ void group_bbox(const float* __restrict__ flow, int b, int gx0, int gy0, int H, int W, int Hs,
+                                           int Ws, int lane, bool align_x8, int& x0, int& y0, int& x1, int& y1) {
+    TileFlow r;
+    tile_flow_load(flow, b, gx0, gy0, H, W, lane, r);
+    tile_bbox_reduce<K>(r, gx0, gy0, H, W, Hs, Ws, lane, align_x8, x0, y0, x1, y1);
 }
 
 // Collapsed window of one (regular) pixel: w[r][s] multiplies source position (Y0 + r, X0 + s).
