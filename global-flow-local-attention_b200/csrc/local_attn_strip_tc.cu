@@ -93,7 +93,10 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
                        const float* __restrict__ flow, const __nv_bfloat16* __restrict__ logits,
                        __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ probs,
                        const __nv_bfloat16* __restrict__ prev, const __nv_bfloat16* __restrict__ mask, int B, int C, int Hs,
-                       int Ws, int H, int W, int ts) {
+                       int Ws, int H, int W, int ts, int knobs) {
+    // `knobs` (environment GFLA_TC_KNOBS, default 0 = production) switch parts of the pipeline off for timing experiments
+    // (results are wrong when set): bit 8 no output stores, bit 10 no weight scatter (slabs only zeroed), bit 11 no slab
+    // writes at all, bit 12 no MMAs, bit 13 no TMA loads.
     using SM = StripSmem<CN>;
     constexpr int NSTAGE = SM::NSTAGE, FBW = ST_FBW, RCH = ST_RCH;
     constexpr int K1 = K + 1, KK = K * K;
@@ -110,7 +113,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_TMEM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long t_start = clock64();
+    const long long t_start = tc_profile_clock();
     StripGeom geo;
     geo.gxn = (W + GW - 1) / GW;
     geo.gyn = (H + GH - 1) / GH;
@@ -178,7 +181,8 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
                     if (strip_skipped(t, j)) continue;
                     const int slot = it % NSTAGE;
                     mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x000200 | slot, it);
-                    if (lane == 0) {
+                    if (lane == 0 && (knobs & 8192)) mbar_arrive(&full_s[slot]);
+                    if (lane == 0 && !(knobs & 8192)) {
                         mbar_arrive_expect_tx(&full_s[slot], SM::S_STAGE);
 #pragma unroll
                         for (int rr = 0; rr < RCH; ++rr) {
@@ -193,7 +197,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
                     ++it;
                 }
             k0 = t.s0; k1 = t.s1;
-            const long long tb0 = clock64();
+            const long long tb0 = tc_profile_clock();
             box0 = box1;
             if (pend) {
                 tile_bbox_reduce<K>(fr, pend_it.gx * GW, pend_it.ty * GH, H, W, Hs, Ws, lane, false, box1.x0, box1.y0, box1.x1, box1.y1);
@@ -207,7 +211,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
                 pend_it = ld;
                 ld.next(geo, ustride);
             }
-            tc_profile_add(0, 6, clock64() - tb0);          // box of tile n+2, flow loads of tile n+3
+            tc_profile_add(0, 6, tc_profile_clock() - tb0);          // box of tile n+2, flow loads of tile n+3
         }
     } else if (warp == 1) {
         // ================================================================= MMA issuer
@@ -242,7 +246,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
                         const uint32_t b0 = smem_u32(smem + SM::OFF_S + slot * SM::S_STAGE);
 #pragma unroll
                         for (int sub = 0; sub < 2; ++sub) {
-                            if (sub == 1 && !shared) break;
+                            if ((sub == 1 && !shared) || (knobs & 4096)) break;
                             const uint32_t d_tmem = tmem_base + (sub == 0 ? buf : (buf ^ 1)) * CN;
                             const bool fresh = sub == 0 ? !started : !next_started;
 #pragma unroll
@@ -330,7 +334,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
         }
         for (TileIt cur = first; cur.ok(geo); cur.next(geo, ustride), ++ti) {
             const uint32_t wsm_cur = wsm_base + (ti & 1) * SM::W_TILE, wsm_nxt = wsm_base + ((ti + 1) & 1) * SM::W_TILE;
-            const long long tw0 = clock64();
+            const long long tw0 = tc_profile_clock();
             const bool have_n = pend;             // this CTA's next tile (same strip or not): its window is built now
             if (pend) nlive = make_window(pend_it, wsm_nxt, nX0, nY0);
             pend = ld.ok(geo);
@@ -339,27 +343,29 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
                 pend_it = ld;
                 ld.next(geo, ustride);
             }
-            tc_profile_add(2, 6, clock64() - tw0);          // window of tile n+1, loads of tile n+2
+            tc_profile_add(2, 6, tc_profile_clock() - tw0);          // window of tile n+1, loads of tile n+2
             mbar_wait(&info_full[ti % ST_NINFO], (ti / ST_NINFO) & 1, 0x020500, ti);
             const StripTile t = infos[ti % ST_NINFO];
             long long fill_cycles = 0;
             for (int cb = 0; cb < t.ncb; ++cb) {
                 const int e0 = X0 - (t.xs + cb * FBW), e0n = nX0 - (t.xs + cb * FBW);   // box position of window column 0
-                const bool cols_hit = live && e0 > -K1 && e0 < FBW;
-                const bool cols_hit_n = have_n && nlive && e0n > -K1 && e0n < FBW;
+                const bool cols_hit = live && e0 > -K1 && e0 < FBW && !(knobs & 1024);
+                const bool cols_hit_n = have_n && nlive && e0n > -K1 && e0n < FBW && !(knobs & 1024);
                 for (int j = t.j0; j <= t.j1; ++j) {
                     if (strip_skipped(t, j)) continue;
                     const int slot = it % NSTAGE;
                     mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x020200 | slot, it);
-                    const long long tf0 = clock64();
+                    const long long tf0 = tc_profile_clock();
                     const uint32_t a_stage = a_base + slot * SM::A_STAGE;
                     const int R0 = 2 * j;
                     bool wrote = false;
+                    if (!(knobs & 2048)) {
 #pragma unroll
                     for (int rr = 0; rr < RCH; ++rr)
                         wrote |= fill_slab_row<K, FBW>(a_stage + rr * SM::FA_SLAB, swz, wsm_cur, cols_hit, (R0 + rr) - Y0, e0, dirty,
                                                   1u << ((slot * RCH + rr) * 2));
-                    if (strip_shared(t, j)) {   // only inside a strip: the next tile is the one whose window was just built
+                    }
+                    if (strip_shared(t, j) && !(knobs & 2048)) {   // only inside a strip: the next tile is the one whose window was just built
 #pragma unroll
                         for (int rr = 0; rr < RCH; ++rr)
                             wrote |= fill_slab_row<K, FBW>(a_stage + SM::A_TILE + rr * SM::FA_SLAB, swz, wsm_nxt, cols_hit_n,
@@ -367,7 +373,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
                     }
                     if (wrote) fence_proxy_async_smem();
                     mbar_arrive(&full_a[slot]);
-                    fill_cycles += clock64() - tf0;
+                    fill_cycles += tc_profile_clock() - tf0;
                     ++it;
                 }
             }
@@ -395,7 +401,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
                 const int buf = ti & 1;
                 mbar_wait(&acc_full[buf], (ti >> 1) & 1, 0x030300 | buf, ti);
                 tc_fence_after();
-                const long long te0 = clock64();
+                const long long te0 = tc_profile_clock();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * CN;
                 __nv_bfloat16* o = out + ((long long)b * hw + pofs) * C + c0;
                 // optional fused mask blend (generator.py:130): out = prev * (1 - mask) + attention * mask
@@ -406,7 +412,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
                     uint32_t v[32];
                     tmem_ld_32x32(taddr + cc * 32, v);
                     tmem_ld_wait();
-                    if (valid && regular) {
+                    if (valid && regular && !(knobs & 256)) {
                         if (pv != nullptr) {   // blend in fp32 before the single rounding to bf16
                             const uint4* p4 = reinterpret_cast<const uint4*>(pv + cc * 32);
 #pragma unroll
@@ -438,7 +444,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
-                tc_profile_add(3, 6, clock64() - te0);          // TMEM -> registers -> global
+                tc_profile_add(3, 6, tc_profile_clock() - te0);          // TMEM -> registers -> global
                 // irregular pixels (fp32 rounding of (flow+offset)+coord straddling an integer, ~1e-5 of all pixels): the
                 // reference's literal 4-taps-per-(i,j) arithmetic, the warp shares one pixel (lanes split the channels)
                 unsigned todo = __ballot_sync(0xffffffffu, valid && !regular);
@@ -484,7 +490,8 @@ static int launch_strip(const void* src, const void* flow, const void* logits, v
     dim3 grid((unsigned)min(units, sm_count()), (unsigned)(C / CN));
     kern<<<grid, ST_THREADS, StripSmem<CN>::ALLOC, st_>>>(tmap, (const __nv_bfloat16*)src, (const float*)flow,
                                                           (const __nv_bfloat16*)logits, (__nv_bfloat16*)out, (__nv_bfloat16*)probs,
-                                                          (const __nv_bfloat16*)prev, (const __nv_bfloat16*)mask, B, C, Hs, Ws, H, W, ts);
+                                                          (const __nv_bfloat16*)prev, (const __nv_bfloat16*)mask, B, C, Hs, Ws, H, W, ts,
+                                                          tune_knob("GFLA_TC_KNOBS", 0));
     return launch_status();
 }
 

@@ -99,7 +99,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_TMEM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long t_start = clock64();
+    const long long t_start = tc_profile_clock();
     const int gxn = (W + GW - 1) / GW, gyn = (H + GH - 1) / GH;
     const int ngroups = B * gyn * gxn;
     const int c0 = blockIdx.y * CN;
@@ -134,9 +134,9 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             // rows yet, so pull them into L2 now -- a whole group of time before the TMA loads need them
             const int gn = g + gridDim.x;
             if (gn < ngroups) {
-                const long long tb0 = clock64();
+                const long long tb0 = tc_profile_clock();
                 bbox_of(gn, nx0, ny0, nx1, ny1);
-                tc_profile_add(0, 6, clock64() - tb0);      // next group's bounding box
+                tc_profile_add(0, 6, tc_profile_clock() - tb0);      // next group's bounding box
                 const int bn = gn / (gxn * gyn), prow = ny1 - ny0 + 1;
                 if ((knobs & 255) == 2 && NHWC && CN == C) {
                     // channels-last, all channels in this CTA: a row segment of the box is one contiguous range
@@ -239,7 +239,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             const bool valid = px < W && py < H;
             int X0 = 0, Y0 = 0;
             bool live = false;
-            const long long tw0 = clock64();
+            const long long tw0 = tc_profile_clock();
             if (valid && !(knobs & 512)) {   // bit 9: timing experiment, skip the per-pixel window construction
                 const long long pofs = (long long)py * W + px;
                 float p[KK];
@@ -258,7 +258,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                     store_window_words<K>(wsm_a, w);
                 }
             }
-            tc_profile_add(2, 6, clock64() - tw0);          // window construction
+            tc_profile_add(2, 6, tc_profile_clock() - tw0);          // window construction
             mbar_wait(&info_full[gi % NINFO], (gi / NINFO) & 1, 0x020500, gi);
             const GroupInfo inf = infos[gi % NINFO];
             long long fill_cycles = 0;
@@ -268,7 +268,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                 for (int rc = 0; rc < inf.nrc; ++rc, ++it) {
                     const int slot = it % NSTAGE;
                     mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x020200 | slot, it);
-                    const long long tf0 = clock64();
+                    const long long tf0 = tc_profile_clock();
                     const uint32_t a_stage = a_base + slot * SM::A_STAGE;
                     const int R0 = inf.y0 + rc * RCH;
                     bool wrote = false;
@@ -278,7 +278,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                                                   1u << (slot * RCH + rr));
                     if (wrote) fence_proxy_async_smem();
                     mbar_arrive(&full_a[slot]);
-                    fill_cycles += clock64() - tf0;
+                    fill_cycles += tc_profile_clock() - tf0;
                 }
             }
             tc_profile_add(2, 7, fill_cycles);              // slab fills
@@ -303,7 +303,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             const int buf = gi & 1;
             mbar_wait(&acc_full[buf], (gi >> 1) & 1, 0x030300 | buf, gi);
             tc_fence_after();
-            const long long te0 = clock64();
+            const long long te0 = tc_profile_clock();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * CN;
             __nv_bfloat16* o = NHWC ? out + ((long long)b * hw + pofs) * C + c0 : out + ((long long)b * C + c0) * hw + pofs;
             // optional fused mask blend (generator.py:130): out = prev * (1 - mask) + attention * mask
@@ -358,7 +358,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            tc_profile_add(3, 6, clock64() - te0);          // TMEM -> registers -> global
+            tc_profile_add(3, 6, tc_profile_clock() - te0);          // TMEM -> registers -> global
             // irregular pixels keep the reference's literal 4-tap arithmetic; the warp shares each one (tile_window.cuh)
             unsigned todo = __ballot_sync(0xffffffffu, valid && !regular);
             while (todo) {

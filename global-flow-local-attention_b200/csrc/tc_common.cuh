@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "gfla_warp.h"
+
 namespace gfla {
 namespace tc {
 
@@ -48,21 +50,16 @@ static __device__ __noinline__ void mbar_timeout(uint32_t tag, uint32_t parity, 
     }
     __trap();
 }
-// Wait profile (debug, off by default): cycles that lane 0 of every warp spent blocked, per (role, barrier kind) of
-// the tag; slot 7 of role 0 = total kernel cycles summed over the CTAs.  Read through gfla_debug_wait_profile().
+// Wait profile (debug builds only: GFLA_BUILD_PROFILE=1 python -m gfla_b200.build, i.e. -DGFLA_TC_PROFILE): cycles that
+// lane 0 of every warp spent blocked, per (role, barrier kind) of the tag, plus explicit region timers (kinds 6, 7);
+// slot 7 of role 0 = total kernel cycles summed over the CTAs.  Read through gfla_debug_wait_profile().
+#ifdef GFLA_TC_PROFILE
 static __device__ unsigned long long g_tc_prof[32];
 static __device__ int g_tc_prof_on = 0;
-
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0, uint32_t iter = 0) {
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {   // try_wait itself suspends the thread for a while before giving up
-        if (clock64() - t0 > 2000000000LL) mbar_timeout(tag, parity, iter);  // ~1 s
-    }
-    const long long dt = clock64() - t0;
-    if (dt > 64 && g_tc_prof_on && (threadIdx.x & 31) == 0)
-        atomicAdd(&g_tc_prof[((tag >> 16) & 3) * 8 + ((tag >> 8) & 7)], static_cast<unsigned long long>(dt));
+__device__ __forceinline__ void tc_profile_add(int role, int kind, long long cycles) {   // call from every lane or lane 0
+    if (g_tc_prof_on && (threadIdx.x & 31) == 0) atomicAdd(&g_tc_prof[role * 8 + kind], static_cast<unsigned long long>(cycles));
 }
-// host side of the wait profile for the translation unit that includes this header
+__device__ __forceinline__ long long tc_profile_clock() { return clock64(); }
 inline int tc_wait_profile(int enable, unsigned long long* out32) {
     cudaError_t e = cudaSuccess;
     if (out32 != nullptr) e = cudaMemcpyFromSymbol(out32, g_tc_prof, sizeof(unsigned long long) * 32);
@@ -73,12 +70,30 @@ inline int tc_wait_profile(int enable, unsigned long long* out32) {
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_tc_prof_on, &enable, sizeof(int));
     return static_cast<int>(e);
 }
-// explicit region timers for the same profile (kinds 6, 7 of a role): call from lane 0 of a warp
-__device__ __forceinline__ void tc_profile_add(int role, int kind, long long cycles) {
-    if (g_tc_prof_on && (threadIdx.x & 31) == 0) atomicAdd(&g_tc_prof[role * 8 + kind], static_cast<unsigned long long>(cycles));
-}
+#else
+__device__ __forceinline__ void tc_profile_add(int, int, long long) {}
+__device__ __forceinline__ long long tc_profile_clock() { return 0; }
+inline int tc_wait_profile(int, unsigned long long*) { return GFLA_E_NOTSUP; }
+#endif
 __device__ __forceinline__ void tc_profile_total(long long t_start) {
-    if (g_tc_prof_on && threadIdx.x == 0) atomicAdd(&g_tc_prof[7], static_cast<unsigned long long>(clock64() - t_start));
+    if (threadIdx.x == 0) tc_profile_add(0, 7, tc_profile_clock() - t_start);
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0, uint32_t iter = 0) {
+#ifdef GFLA_TC_PROFILE
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {   // try_wait itself suspends the thread for a while before giving up
+        if (clock64() - t0 > 2000000000LL) mbar_timeout(tag, parity, iter);
+    }
+    const long long dt = clock64() - t0;
+    if (dt > 64) tc_profile_add((tag >> 16) & 3, (tag >> 8) & 7, dt);
+#else
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 2000000000LL) mbar_timeout(tag, parity, iter);  // ~1 s
+    }
+#endif
 }
 
 // explicit shared-space accesses (32-bit shared addresses): keeps ptxas from falling back to generic LD/ST
