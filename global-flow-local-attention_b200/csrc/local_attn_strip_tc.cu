@@ -427,17 +427,15 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
                                 }
                             }
                         }
-                        uint4* o4 = reinterpret_cast<uint4*>(o + cc * 32);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            uint4 pk;
-                            __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
-                            __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
-                            __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
-                            __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
-                            pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                            __stcs(o4 + i, pk);   // streaming store: written once, never re-read by this kernel
+                        for (int i = 0; i < 2; ++i) {   // 2 x 32 bytes: written once, never re-read by this kernel
+                            uint32_t pk[8];
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj) {
+                                const __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[16 * i + 2 * jj]), __uint_as_float(v[16 * i + 2 * jj + 1]));
+                                pk[jj] = *reinterpret_cast<const uint32_t*>(&t2);
+                            }
+                            stg256_cs(o + cc * 32 + i * 16, pk);
                         }
                     }
                 }

@@ -452,7 +452,8 @@ int local_attn_fwd_tc(const void* src, const void* flow, const void* logits, voi
     const int cn = pick_cn(C);
     const bool nhwc = layout == GFLA_NHWC;
     const int strip = tc::tune_knob("GFLA_TC_STRIP", kStripDefault);
-    if (nhwc && strip >= 0) return local_attn_fwd_strip_tc(src, flow, logits, out, probs, prev, mask, B, C, Hs, Ws, H, W, k, strip, st_);
+    if (nhwc && strip >= 0 && aligned(out, 32))   // the strip kernel's epilogue stores 32 bytes per lane
+        return local_attn_fwd_strip_tc(src, flow, logits, out, probs, prev, mask, B, C, Hs, Ws, H, W, k, strip, st_);
 #define GFLA_TC_CASE(K_, CN_)                                                                                        \
     if (k == K_ && cn == CN_)                                                                                        \
         return nhwc ? tc::launch_tc<K_, CN_, true>(src, flow, logits, out, probs, prev, mask, B, C, Hs, Ws, H, W, st_)  \

@@ -110,6 +110,12 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) {
     return v;
 }
 
+// 32-byte streaming global store (sm_100 256-bit STG): one full sector per lane instead of two half-sector writes
+__device__ __forceinline__ void stg256_cs(void* gptr, const uint32_t (&w)[8]) {
+    asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(gptr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                 "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
