@@ -42,7 +42,9 @@ struct StripSmem {
     static constexpr int OFF_S = 0;
     static constexpr int OFF_A = OFF_S + NSTAGE * S_STAGE;
     static constexpr int OFF_W = OFF_A + NSTAGE * A_STAGE;
-    static constexpr int OFF_INFO = OFF_W + 2 * W_TILE;
+    static constexpr int O_WARP = 32 * 64;                     // output staging of one epilogue warp: [32 pixels][32 channels] bf16
+    static constexpr int OFF_O = OFF_W + 2 * W_TILE;           // 64B-swizzled: 512-byte aligned
+    static constexpr int OFF_INFO = OFF_O + 4 * O_WARP;
     static constexpr int OFF_BAR = OFF_INFO + ST_NINFO * 32;
     static constexpr int NBAR = 3 * NSTAGE + 4 + ST_NINFO;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
@@ -51,6 +53,7 @@ struct StripSmem {
 };
 static_assert(sizeof(StripTile) == 32, "StripTile is stored in 32-byte info slots");
 static_assert(StripSmem<256>::ALLOC <= 232448, "shared memory budget");
+static_assert(StripSmem<256>::OFF_O % 512 == 0 && StripSmem<128>::OFF_O % 512 == 0 && StripSmem<64>::OFF_O % 512 == 0, "staging alignment");
 
 // strips: units of `ts` vertically adjacent tiles; unit -> (b, gx, first tile row, end tile row)
 struct StripGeom {
@@ -89,7 +92,8 @@ struct TileIt {
 
 template <int K, int CN>
 __global__ void __launch_bounds__(ST_THREADS, 1)
-k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfloat16* __restrict__ src,
+k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __grid_constant__ CUtensorMap tmap_out,
+                       const __nv_bfloat16* __restrict__ src,
                        const float* __restrict__ flow, const __nv_bfloat16* __restrict__ logits,
                        __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ probs,
                        const __nv_bfloat16* __restrict__ prev, const __nv_bfloat16* __restrict__ mask, int B, int C, int Hs,
@@ -129,6 +133,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
         for (int i = 0; i < ST_NINFO; ++i) mbar_init(&info_full[i], 1);
         fence_barrier_init();
         tma_prefetch_desc(&tmap_src);
+        tma_prefetch_desc(&tmap_out);
     }
     if (warp == 1) tmem_alloc(tmem_slot, 2 * CN >= 32 ? 2 * CN : 32);
     tc_fence_before();
@@ -403,49 +408,66 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
                 tc_fence_after();
                 const long long te0 = tc_profile_clock();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * CN;
-                __nv_bfloat16* o = out + ((long long)b * hw + pofs) * C + c0;
                 // optional fused mask blend (generator.py:130): out = prev * (1 - mask) + attention * mask
-                const __nv_bfloat16* pv = prev == nullptr ? nullptr : prev + ((long long)b * hw + pofs) * C + c0;
-                const float mk = (prev != nullptr && valid) ? __bfloat162float(mask[(long long)b * hw + pofs]) : 1.f;
+                const __nv_bfloat16* pv = (prev == nullptr || !valid) ? nullptr : prev + ((long long)b * hw + pofs) * C + c0;
+                const float mk = pv != nullptr ? __bfloat162float(mask[(long long)b * hw + pofs]) : 1.f;
+                // The warp's 32 pixels (2 rows x 16) go out as ONE tensor tile per 32 channels: registers -> 64B-swizzled
+                // staging -> TMA store.  Per-lane global stores would touch 32 different lines per instruction, and that
+                // store path, not HBM, was the largest single cost of the kernel.  The TMA clips the tile at the image edge;
+                // irregular pixels (zero weights -> zeros here) are overwritten below.
+                const uint32_t ob = smem_u32(smem + SM::OFF_O) + q * SM::O_WARP;
+                const uint32_t orow = ob + lane * 64, oswz = (lane >> 1) & 3;
 #pragma unroll 1
                 for (int cc = 0; cc < CN / 32; ++cc) {
                     uint32_t v[32];
                     tmem_ld_32x32(taddr + cc * 32, v);
                     tmem_ld_wait();
-                    if (valid && regular && !(knobs & 256)) {
-                        if (pv != nullptr) {   // blend in fp32 before the single rounding to bf16
-                            const uint4* p4 = reinterpret_cast<const uint4*>(pv + cc * 32);
+                    if (cc == CN / 32 - 1) {   // accumulator fully read: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                    }
+                    if (pv != nullptr) {   // blend in fp32 before the single rounding to bf16
+                        const uint4* p4 = reinterpret_cast<const uint4*>(pv + cc * 32);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const uint4 pq = p4[i];
-                                const uint32_t pw[4] = {pq.x, pq.y, pq.z, pq.w};
+                        for (int i = 0; i < 4; ++i) {
+                            const uint4 pq = p4[i];
+                            const uint32_t pw[4] = {pq.x, pq.y, pq.z, pq.w};
 #pragma unroll
-                                for (int jj = 0; jj < 4; ++jj) {
-                                    const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pw[jj]));
-                                    v[8 * i + 2 * jj] = __float_as_uint(pf.x * (1.f - mk) + __uint_as_float(v[8 * i + 2 * jj]) * mk);
-                                    v[8 * i + 2 * jj + 1] = __float_as_uint(pf.y * (1.f - mk) + __uint_as_float(v[8 * i + 2 * jj + 1]) * mk);
-                                }
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pw[jj]));
+                                v[8 * i + 2 * jj] = __float_as_uint(pf.x * (1.f - mk) + __uint_as_float(v[8 * i + 2 * jj]) * mk);
+                                v[8 * i + 2 * jj + 1] = __float_as_uint(pf.y * (1.f - mk) + __uint_as_float(v[8 * i + 2 * jj + 1]) * mk);
                             }
-                        }
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {   // 2 x 32 bytes: written once, never re-read by this kernel
-                            uint32_t pk[8];
-#pragma unroll
-                            for (int jj = 0; jj < 8; ++jj) {
-                                const __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[16 * i + 2 * jj]), __uint_as_float(v[16 * i + 2 * jj + 1]));
-                                pk[jj] = *reinterpret_cast<const uint32_t*>(&t2);
-                            }
-                            stg256_cs(o + cc * 32 + i * 16, pk);
                         }
                     }
+                    if (lane == 0) bulk_wait_read<0>();   // the previous tile store has finished reading the staging buffer
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[8 * i + 2 * jj]), __uint_as_float(v[8 * i + 2 * jj + 1]));
+                            pk[jj] = *reinterpret_cast<const uint32_t*>(&t2);
+                        }
+                        sts128(orow + ((i ^ oswz) << 4), pk[0], pk[1], pk[2], pk[3]);
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && !(knobs & 256)) {
+                        tma_store_4d(&tmap_out, ob, c0 + cc * 32, gx * GW, ty * GH + 2 * q, b);
+                        bulk_commit();
+                    }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[buf]);
-                tc_profile_add(3, 6, tc_profile_clock() - te0);          // TMEM -> registers -> global
+                tc_profile_add(3, 6, tc_profile_clock() - te0);          // TMEM -> registers -> staging -> TMA store
                 // irregular pixels (fp32 rounding of (flow+offset)+coord straddling an integer, ~1e-5 of all pixels): the
                 // reference's literal 4-taps-per-(i,j) arithmetic, the warp shares one pixel (lanes split the channels)
                 unsigned todo = __ballot_sync(0xffffffffu, valid && !regular);
+                if (todo) {   // the tile stores above must have landed before these pixels are rewritten
+                    if (lane == 0) bulk_wait<0>();
+                    __syncwarp();
+                }
                 while (todo) {
                     const int src_lane = __ffs(todo) - 1;
                     todo &= todo - 1;
@@ -456,6 +478,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __nv_
             }
         }
     }
+    if (warp >= 6 && lane == 0) bulk_wait_read<0>();   // staging buffers stay valid until their last store has read them
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 2 * CN >= 32 ? 2 * CN : 32);
@@ -476,6 +499,14 @@ static int launch_strip(const void* src, const void* flow, const void* logits, v
     if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return GFLA_E_NOTSUP;
+    // out (c, x, y, b), box [32 c][16 x][2 y]: what one epilogue warp stores per step; 64-byte rows, 64B swizzle
+    CUtensorMap tmap_o;
+    const cuuint64_t odim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t ostr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    const cuuint32_t obox[4] = {32, GW, 2, 1};
+    if (enc(&tmap_o, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, odim, ostr, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return GFLA_E_NOTSUP;
     auto kern = k_local_attn_fwd_strip<K, CN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, StripSmem<CN>::ALLOC);
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -486,7 +517,7 @@ static int launch_strip(const void* src, const void* flow, const void* logits, v
     }
     const int units = B * gxn * ((gyn + ts - 1) / ts);
     dim3 grid((unsigned)min(units, sm_count()), (unsigned)(C / CN));
-    kern<<<grid, ST_THREADS, StripSmem<CN>::ALLOC, st_>>>(tmap, (const __nv_bfloat16*)src, (const float*)flow,
+    kern<<<grid, ST_THREADS, StripSmem<CN>::ALLOC, st_>>>(tmap, tmap_o, (const __nv_bfloat16*)src, (const float*)flow,
                                                           (const __nv_bfloat16*)logits, (__nv_bfloat16*)out, (__nv_bfloat16*)probs,
                                                           (const __nv_bfloat16*)prev, (const __nv_bfloat16*)mask, B, C, Hs, Ws, H, W, ts,
                                                           tune_knob("GFLA_TC_KNOBS", 0));
