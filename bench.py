@@ -355,7 +355,7 @@ def main():
                 "frac": ach / peak, "traffic": traffic.get(tkey) if args.layout == "nhwc" and args.flow == "smooth" else None,
                 "algorithmic_bytes": nbytes, "launch_ms": ms}
 
-    rf_fwd = roof(fwd_bytes, fwd_ms, "k_local_attn_fwd_tc (fused forward)", "fwd")
+    rf_fwd = roof(fwd_bytes, fwd_ms, "k_local_attn_fwd_strip (fused forward)", "fwd")
     rf_bwd = roof(bwd_bytes, bwd_ms, "k_local_attn_bwd_gs_tc + k_local_attn_bwd_q_tc (+ grad_source memset)", "bwd")
     # The step is three tile kernels of similar weight (ncu launch list, profiles/r1_bench_launches.md:
     # grad_flow/logits 36 %, forward 34 %, grad_source 30 %).  `roofline` describes the fused FORWARD kernel --

@@ -443,7 +443,7 @@ int local_attn_fwd_strip_tc(const void*, const void*, const void*, void*, void*,
 
 // Channels-last inputs run the strip schedule (local_attn_strip_tc.cu).  GFLA_TC_STRIP: -1 = per-tile kernel of this
 // file instead, 0 = strip length chosen per launch, n > 0 = n tiles per strip.
-constexpr int kStripDefault = -1;
+constexpr int kStripDefault = 0;
 
 int local_attn_fwd_tc(const void* src, const void* flow, const void* logits, void* out, void* probs, const void* prev,
                       const void* mask, int B, int C, int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype,
