@@ -50,7 +50,7 @@ static __device__ __noinline__ void mbar_timeout(uint32_t tag, uint32_t parity, 
     }
     __trap();
 }
-// Wait profile (debug builds only: GFLA_BUILD_PROFILE=1 python -m gfla_b200.build, i.e. -DGFLA_TC_PROFILE): cycles that
+// Wait profile (debug builds only: GFLA_BUILD_PROFILE=1 python build.py, i.e. -DGFLA_TC_PROFILE): cycles that
 // lane 0 of every warp spent blocked, per (role, barrier kind) of the tag, plus explicit region timers (kinds 6, 7);
 // slot 7 of role 0 = total kernel cycles summed over the CTAs.  Read through gfla_debug_wait_profile().
 #ifdef GFLA_TC_PROFILE
