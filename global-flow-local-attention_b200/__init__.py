@@ -8,15 +8,18 @@ name ``gfla_b200``.  Public surface = the reference's own classes:
     LocalAttnReshape / LocalAttnReshapeFunction    (local_attn_reshape.py)
     Resample2d / Resample2dFunction                (resample2d.py)
     ExtractorAttn                                  (base_function.py:790-818)
+    AffineRegularizationLoss / MultiAffineRegularizationLoss   (external_function.py:12-77)
 plus the fused op ``local_attention`` / ``LocalAttnFunction`` and
 ``compat.install()`` for the legacy extension-module names.
 """
 from .block_extractor import BlockExtractor, BlockExtractorFunction
 from .extractor_attn import ExtractorAttn, LocalAttnFunction, local_attention
 from .local_attn_reshape import LocalAttnReshape, LocalAttnReshapeFunction
+from .losses import AffineRegularizationLoss, MultiAffineRegularizationLoss
 from .resample2d import Resample2d, Resample2dFunction
-from . import compat, functional, sharding  # noqa: F401
+from . import compat, functional, losses, sharding  # noqa: F401
 
 __all__ = ["BlockExtractor", "BlockExtractorFunction", "LocalAttnReshape", "LocalAttnReshapeFunction", "Resample2d",
-           "Resample2dFunction", "ExtractorAttn", "LocalAttnFunction", "local_attention", "compat", "functional",
+           "Resample2dFunction", "ExtractorAttn", "LocalAttnFunction", "local_attention", "AffineRegularizationLoss",
+           "MultiAffineRegularizationLoss", "compat", "functional",
            "sharding"]

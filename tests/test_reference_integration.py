@@ -45,3 +45,35 @@ def test_reference_generators_build_on_our_ops(fuse):
                             'target.attn0.fully_connect_layer.2.bias', 'target.attn0.fully_connect_layer.2.weight'])
     assert lines[2] == "3 5"       # attn_layer=2,3 with kernel_size 2=5,3=3: level 3 (first built) k=3, level 2 k=5
     assert lines[3] == "True"
+
+
+LOSS_SCRIPT = r"""
+import sys, types, warnings
+warnings.simplefilter("ignore")
+sys.path.insert(0, %r)
+import numpy as np, torch
+import gfla_b200
+gfla_b200.compat.install(reference_root=%r)
+util = types.ModuleType("util"); util.util = types.ModuleType("util.util")     # external_function.py:8 (imageio & co. are absent here)
+sys.modules["util"] = util; sys.modules["util.util"] = util.util
+from model.networks import external_function as ef
+for kz in (3, 4, 5):
+    ref, ours = ef.AffineRegularizationLoss(kz), gfla_b200.AffineRegularizationLoss(kz)
+    print(float((ref.kernel - ours.kernel).abs().max()), tuple(ref.kernel.shape) == tuple(ours.kernel.shape))
+    flow = torch.randn(2, 2, 9, 11)
+    print(float((ref.flow2grid(flow) - ours.flow2grid(flow)).abs().max()))
+m = ef.MultiAffineRegularizationLoss({'2': 5, '3': 3}); o = gfla_b200.MultiAffineRegularizationLoss({'2': 5, '3': 3})
+print(m.layers == o.layers, [m.method_dic[k].kz for k in m.layers] == [o.method_dic[k].kz for k in o.layers])
+"""
+
+
+def test_regularization_loss_constants_match_the_reference_class():
+    """the reference's AffineRegularizationLoss itself needs a GPU (its two custom ops); its constants and grid do not"""
+    out = subprocess.run([sys.executable, "-c", LOSS_SCRIPT % (ROOT, REF)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.strip().splitlines()
+    for i in range(3):
+        err, same_shape = lines[2 * i].split()
+        assert float(err) < 1e-12 and same_shape == "True"
+        assert float(lines[2 * i + 1]) == 0.0
+    assert lines[6] == "True True"
