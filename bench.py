@@ -119,47 +119,165 @@ def make_inputs(torch, dev, B, C, H, W, k, seed, flow_kind="smooth"):
 
 
 # ----------------------------------------------------------------------------- CPU reference leg
-def cpu_reference_run(steps, warmup, budget_s, full=True):
+REF_ROWS = 64      # fixed strip of the 256x256 map that one reference step processes (bounded sample)
+
+
+def host_flow(np, torch, rng, kind, rows, W):
+    """the same two flow families as the GPU arm (make_inputs): smooth = x16 bilinear up-sampling of U(-8,8), iid = U(-8,8)"""
+    if kind == "smooth":
+        coarse = torch.from_numpy(rng.uniform(-8, 8, (1, 2, max(rows // 16, 2), W // 16)))
+        return torch.nn.functional.interpolate(coarse, size=(rows, W), mode="bilinear", align_corners=True).numpy().astype(np.float32)
+    return rng.uniform(-8, 8, (1, 2, rows, W)).astype(np.float32)
+
+
+def cpu_reference_run(steps, warmup, flow_kind="smooth", rows=REF_ROWS):
     """Times the reference's CPU implementation of the path (its own kernel bodies compiled
     for the host + torch CPU ops for softmax/mul/avg_pool, oracle/ref_pipeline.py) on a bounded
-    sample of the cfg2 workload: B=1, full C=256, k=5, a strip of R rows x 256 columns, fp32
-    (the reference has no bf16).  Returns per-step seconds and the sample description."""
+    sample of the cfg2 workload: B=1, full C=256, k=5, a FIXED strip of `rows` rows x 256 columns, fp32
+    (the reference has no bf16), the same flow family as the GPU arm.  Thread count is set explicitly
+    (torchrun exports OMP_NUM_THREADS=1): the host build's atomics (`#pragma omp atomic` standing in for
+    atomicAdd) collide C*k*k-fold on grad_flow, so more threads are not always faster -- a short probe picks
+    the better of {1, all cores} and `cores` states what the timed steps used.
+    Returns the cpu_baseline dict and per-step seconds."""
     import numpy as np
     import torch
     import oracle.oracle as orc
     from oracle.ref_pipeline import local_attn_fwd_bwd
+    ncpu = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     if orc.have_ref():
         lib, kind = orc.Ref(), "reference"
-        cores = lib.max_threads()
     else:
         orc.build(ref=False)
-        lib, kind, cores = orc.Oracle(), "port", 1
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+        lib, kind = orc.Oracle(), "port"
+    torch.set_num_threads(ncpu)
     C, W, k = CFG["C"], CFG["W"], CFG["k"]
     rng = np.random.default_rng(0)
     src = rng.standard_normal((1, C, CFG["H"], W)).astype(np.float32)
+    flow = host_flow(np, torch, rng, flow_kind, rows, W)
+    logits = rng.standard_normal((1, k * k, rows, W)).astype(np.float32)
+    g = rng.standard_normal((1, C, rows, W)).astype(np.float32)
 
-    def run(rows):
-        flow = rng.uniform(-8, 8, (1, 2, rows, W)).astype(np.float32)
-        logits = rng.standard_normal((1, k * k, rows, W)).astype(np.float32)
-        g = rng.standard_normal((1, C, rows, W)).astype(np.float32)
+    def run(r=rows):
         t = time.perf_counter()
-        local_attn_fwd_bwd(lib, src, flow, logits, g, k)
+        c = np.ascontiguousarray
+        local_attn_fwd_bwd(lib, src, c(flow[:, :, :r]), c(logits[:, :, :r]), c(g[:, :, :r]), k)
         return time.perf_counter() - t
 
-    probe_rows = 4
-    run(probe_rows)                                    # page-in / thread pool warm-up
-    per_row = run(probe_rows) / probe_rows
-    n = max(1, steps + warmup)
-    rows = int(max(2, min(CFG["H"], budget_s / n / max(per_row, 1e-9))))
+    cores = 1
+    if kind == "reference":
+        probe = {}
+        for n in sorted({1, ncpu}):
+            lib.set_threads(n)
+            run(8)                                       # page-in / thread-pool warm-up
+            probe[n] = run(8)
+        cores = min(probe, key=probe.get)
+        lib.set_threads(cores)
     for _ in range(warmup):
-        run(rows)
-    times = [run(rows) for _ in range(steps)]
+        run()
+    times = [run() for _ in range(steps)]
     sec = sum(times) / len(times)
     mpx = rows * W / sec / 1e6
-    return {"value": mpx, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"B=1 C={C} k={k} fp32, strip of {rows} rows x {W} cols of the 256x256 map, fwd+bwd, "
-                      f"{steps} steps (+{warmup} warm-up), unfused reference pipeline"}, sec
+    return {"value": mpx, "unit": UNIT, "cores": cores, "host_cores": ncpu, "kind": kind,
+            "sample": f"B=1 C={C} k={k} fp32, fixed strip of {rows} rows x {W} cols of the 256x256 map, {flow_kind} flow, fwd+bwd, "
+                      f"{steps} steps (+{warmup} warm-up), unfused reference pipeline; threads = best of {{1, {ncpu}}} on an 8-row probe"}, sec
+
+
+def bind_to_gpu_numa_node(torch, local_rank):
+    """pin this process (and so its pinned host buffers, first-touch) to the NUMA node the GPU hangs off"""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        devid = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devid:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
+def _time(torch, fn, warm, n):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+def extras(torch, F_, dev, args, peak, peak_kind):
+    """Extra keys of the N=1 line (each bounded to a fraction of a second of GPU time):
+      iid_flow        the same cfg2 step with iid U(-8,8) flow (adversarial for the tiling)
+      cfg3            BASELINE config 3: resample2d fwd+bwd, B=32 C=128 512x512 fp32, kernel_size 2 (module default) and 4
+                      (what training uses), each with its own HBM roofline (1036 / 1560 algorithmic B per pixel)
+      reference_cuda  the reference's own CUDA kernels recompiled for sm_100a (oracle/_ref/libgfla_ref_cuda.so), running the
+                      unfused ExtractorAttn tail in fp32 on 2 samples of the cfg2 shape -- the same-box GPU baseline"""
+    out = {}
+    B, C, H, W, k = (CFG[x] for x in "BCHWk")
+    cl = torch.channels_last
+    try:
+        src, flow, logits, gout = (t.to(dev) for t in make_inputs(torch, dev, B, C, H, W, k, seed=4321, flow_kind="iid"))
+        src, gout = src.contiguous(memory_format=cl), gout.contiguous(memory_format=cl)
+        f_ms = _time(torch, lambda: F_.local_attn_fwd(src, flow, logits, k), 3, 10)
+        b_ms = _time(torch, lambda: F_.local_attn_bwd(src, flow, logits, gout, k), 3, 10)
+        fb, bb = algorithmic_bytes(B, C, H, W, k)
+        out["iid_flow"] = {"value": B * H * W / ((f_ms + b_ms) * 1e-3) / 1e6, "unit": UNIT, "fwd_ms": f_ms, "bwd_ms": b_ms,
+                           "fwd_frac": fb / (f_ms * 1e-3) / 1e9 / peak, "bwd_frac": bb / (b_ms * 1e-3) / 1e9 / peak, "steps": 10}
+        del src, flow, logits, gout
+    except Exception as exc:
+        out["iid_flow"] = {"error": repr(exc)[:200]}
+    try:
+        Bc, Cc, Hc, Wc = 32, 128, 512, 512
+        g = torch.Generator(device="cpu").manual_seed(5)
+        coarse = torch.rand(Bc, 2, Hc // 16, Wc // 16, generator=g) * 16 - 8
+        flow = torch.nn.functional.interpolate(coarse, size=(Hc, Wc), mode="bilinear", align_corners=True).to(dev)
+        x = torch.randn(Bc, Cc, Hc, Wc, device=dev)
+        go = torch.randn(Bc, Cc, Hc, Wc, device=dev)
+        px = Bc * Hc * Wc
+        c3 = {}
+        for ks, sigma in ((2, 5.0), (4, 2.0)):
+            in2 = torch.cat([flow, torch.full((Bc, 1, Hc, Wc), sigma, device=dev)], 1).contiguous()
+            f_ms = _time(torch, lambda: F_.resample2d_fwd(x, in2, ks, 1), 2, 5)
+            b_ms = _time(torch, lambda: F_.resample2d_bwd(x, in2, go, ks, 1), 2, 5)
+            fwd_b, bwd_b = px * (2 * Cc * 4 + 12), px * (3 * Cc * 4 + 24)
+            c3[f"ks{ks}"] = {"value": px / ((f_ms + b_ms) * 1e-3) / 1e6, "unit": UNIT, "fwd_ms": f_ms, "bwd_ms": b_ms, "sigma": sigma,
+                            "roofline": {"bound": "hbm", "achieved": (fwd_b + bwd_b) / ((f_ms + b_ms) * 1e-3) / 1e9, "peak": peak,
+                                         "peak_source": peak_kind, "unit": "GB/s", "frac": (fwd_b + bwd_b) / ((f_ms + b_ms) * 1e-3) / 1e9 / peak,
+                                         "frac_fwd": fwd_b / (f_ms * 1e-3) / 1e9 / peak, "frac_bwd": bwd_b / (b_ms * 1e-3) / 1e9 / peak}}
+            del in2
+        c3["workload"] = "cfg3: resample2d fwd+bwd, B=32 C=128 512x512 fp32, smooth flow, dilation 1"
+        out["cfg3"] = c3
+        del x, go, flow
+    except Exception as exc:
+        out["cfg3"] = {"error": repr(exc)[:200]}
+    torch.cuda.empty_cache()
+    try:
+        import oracle.ref_cuda as rc
+        if not rc.available():
+            raise FileNotFoundError("oracle/_ref/libgfla_ref_cuda.so not built")
+        nb = 2
+        src, flow, logits, gout = (t.to(dev) for t in make_inputs(torch, dev, nb, C, H, W, k, seed=77, flow_kind=args.flow))
+        s32, l32, g32 = src.float(), logits.float(), gout.float()
+        ms = _time(torch, lambda: rc.local_attn_fwd_bwd(s32, flow, l32, g32, k, chunk=1), 1, 2)
+        out["reference_cuda"] = {"value": nb * H * W / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_sample": ms / nb, "dtype": "f32",
+                                 "kind": "reference CUDA kernels (block_extractor / local_attn_reshape) recompiled for sm_100a + torch softmax/mul/avg_pool",
+                                 "sample": f"{nb} samples of the cfg2 shape (C={C} {H}x{W} k={k}), fwd+bwd, one sample per launch (the reference's int n limit)"}
+    except Exception as exc:
+        out["reference_cuda"] = {"unavailable": repr(exc)[:200]}
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -172,6 +290,11 @@ def main():
     ap.add_argument("--algo", default="auto", choices=["auto", "gather", "tile"])
     ap.add_argument("--layout", default="nhwc", choices=["nhwc", "nchw"],
                     help="storage of the [B,C,H,W] feature tensors: channels_last (default, the tile kernels' fast layout) or contiguous NCHW")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4", "cfg5"],
+                    help="cfg2 (default, the BASELINE metric): fused warp layer fwd+bwd; cfg4 / cfg5: the reference's Pose / Face generator on these ops (bench_models.py)")
+    ap.add_argument("--model-dtype", default="bf16", choices=["bf16", "fp32"], help="cfg4/cfg5: parameter / activation dtype")
+    ap.add_argument("--arms", default="fused,literal,refcuda", help="cfg4/cfg5: comma list, first = the reported value")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra keys (iid flow, cfg3 resample2d, reference CUDA kernels)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -186,12 +309,22 @@ def main():
               "sharding": f"batch x{world} (no data-path collective)",
               "l2": "inputs (>=1 GiB per step) exceed the 126 MB L2; no explicit flush"}
 
+    if args.workload != "cfg2":
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the reference has no CPU path for its generators "
+                                  "(block_extractor.py:23-24 raises on CPU tensors); its CUDA kernels run as the `refcuda` arm of "
+                                  f"`bench.py --workload {args.workload}`"}), flush=True)
+            return 0
+        import bench_models
+        return bench_models.run(args)
+
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return 0
         steps, warmup = max(1, args.steps), max(0, args.warmup)
-        cb, sec = cpu_reference_run(steps, warmup, budget_s=150.0)
+        cb, sec = cpu_reference_run(steps, warmup, flow_kind=args.flow)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -211,6 +344,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(torch, local_rank)      # before any pinned allocation (e2e host buffers)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import torch.distributed as dist
@@ -250,8 +384,10 @@ def main():
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
     barrier()
     t_wall0 = time.time()
+    launches0 = _lib.lib().gfla_debug_launch_count()
     for i in range(steps):
         step(ev[i])
+    launches = int(_lib.lib().gfla_debug_launch_count() - launches0)   # kernels of libgfla_warp.so launched in the timed region
     barrier()
     t_wall1 = time.time()
     total_ms = ev[0][0].elapsed_time(ev[-1][2])
@@ -269,17 +405,18 @@ def main():
         def step_planar():
             F_.local_attn_fwd(src_p, flow, logits, k, algo=args.algo)
             F_.local_attn_bwd(src_p, flow, logits, gout_p, k)
-        for _ in range(2):
+        for _ in range(3):
             step_planar()
         barrier()
         a_, b__ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p_steps = max(steps, 20)
         a_.record()
-        for _ in range(3):
+        for _ in range(p_steps):
             step_planar()
         b__.record()
         barrier()
-        p_ms = reduce_max_time(a_.elapsed_time(b__), dev) / 3
-        nchw = {"value": world * B * H * W / (p_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": p_ms, "steps": 3,
+        p_ms = reduce_max_time(a_.elapsed_time(b__), dev) / p_steps
+        nchw = {"value": world * B * H * W / (p_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": p_ms, "steps": p_steps,
                 "note": "contiguous NCHW feature tensors (the reference's layout), same workload"}
         del src_p, gout_p
 
@@ -293,18 +430,18 @@ def main():
         h2d = sum(t.numel() * t.element_size() for t in (hs, hf, hl, hg))
         d2h = sum(t.numel() * t.element_size() for t in (ho, hgs, hgf, hgl))
 
-        # The batch is processed in 2-sample chunks on 3 streams, so the H2D of chunk i+1 overlaps the kernels and the
-        # D2H of chunk i (PCIe is full duplex; every byte is still copied inside the timed region, through the public
-        # autograd API, once per step).
-        chunks = [(b0, min(B, b0 + 2)) for b0 in range(0, B, 2)]
-        side = [torch.cuda.Stream(device=dev) for _ in range(3)]
+        # The batch is processed in 4-sample chunks alternating between 2 streams, so the H2D of chunk i+1 overlaps the
+        # kernels and the D2H of chunk i (PCIe is full duplex; every byte is still copied inside the timed region, through
+        # the public autograd API, once per step).  Host buffers are pinned on the GPU's own NUMA node (see above).
+        chunks = [(b0, min(B, b0 + 4)) for b0 in range(0, B, 4)]
+        side = [torch.cuda.Stream(device=dev) for _ in range(2)]
 
         def e2e_step():
             main = torch.cuda.current_stream(dev)
             for st in side:
                 st.wait_stream(main)
             for ci, (b0, b1) in enumerate(chunks):
-                with torch.cuda.stream(side[ci % 3]):
+                with torch.cuda.stream(side[ci % 2]):
                     s = hs[b0:b1].to(dev, non_blocking=True).requires_grad_()
                     f = hf[b0:b1].to(dev, non_blocking=True).requires_grad_()
                     l = hl[b0:b1].to(dev, non_blocking=True).requires_grad_()
@@ -330,7 +467,8 @@ def main():
         barrier()
         e2e_ms = reduce_max_time(a.elapsed_time(b_), dev) / e2e_steps
         e2e = {"value": world * B * H * W / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps}
+               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps, "numa_node": numa_node,
+               "chunks": len(chunks), "streams": len(side)}
     if rank == 0:
         sampler.stop()
 
@@ -369,12 +507,13 @@ def main():
             "step_roofline_frac": (fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9 / peak,
             "clocks": sampler.summary(t_wall0, t_wall1),
             "planar_nchw": nchw,
-            "gpu_launches": 3 * steps,   # our kernels per step: forward tile, grad_source tile, grad_flow/logits tile
-                                         # (plus one cudaMemsetAsync node for grad_source, not counted)
+            "gpu_launches": launches,    # counted by the library (gfla_debug_launch_count) across the timed region
             "e2e": e2e}
+    if world == 1 and not args.no_extras:
+        line.update(extras(torch, F_, dev, args, peak, peak_kind))
     if world == 1 and not args.no_cpu_baseline:
         try:
-            cb, _ = cpu_reference_run(steps=2, warmup=0, budget_s=20.0)
+            cb, _ = cpu_reference_run(steps=2, warmup=0, flow_kind=args.flow)
             line["cpu_baseline"] = cb
         except Exception as exc:  # the baseline leg must never take the bench line down
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(exc)}

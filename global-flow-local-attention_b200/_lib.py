@@ -22,6 +22,7 @@ _vp, _i = ctypes.c_void_p, ctypes.c_int
 SIGNATURES = {
     "gfla_abi_version": [],
     "gfla_device_check": [],
+    "gfla_debug_launch_count": [],
     "gfla_debug_set_buffer": [_vp],
     "gfla_debug_wait_profile": [_i, _i, _vp],
     "gfla_relayout": [_vp, _vp] + [_i] * 6 + [_vp],
@@ -56,6 +57,7 @@ def lib() -> ctypes.CDLL:
             fn = getattr(l, name)          # AttributeError if the .so lacks a declared symbol
             fn.argtypes = argtypes
             fn.restype = _i
+        l.gfla_debug_launch_count.restype = ctypes.c_ulonglong
         l.gfla_error_string.argtypes = [_i]
         l.gfla_error_string.restype = ctypes.c_char_p
         if l.gfla_abi_version() != ABI_VERSION:

@@ -25,6 +25,14 @@ int tc_wait_profile_strip(int, unsigned long long*);
 bool local_attn_fwd_tc_supported(int B, int C, int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, int layout, const void* src, const void* out);
 }  // namespace gfla
 
+#include <atomic>
+#include <cstdlib>
+
+namespace gfla {
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace gfla
+
 using namespace gfla;
 
 #define REQ_PTR(p) do { if ((p) == nullptr) return GFLA_E_NULL; } while (0)
@@ -64,6 +72,8 @@ int gfla_debug_wait_profile(int which, int enable, unsigned long long* out_u64x3
     if (e != cudaSuccess) return static_cast<int>(e);
     return which == 0 ? tc_wait_profile_fwd(enable, out_u64x32) : tc_wait_profile_strip(enable, out_u64x32);
 }
+
+unsigned long long gfla_debug_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int gfla_debug_set_buffer(void* host_mapped_u64x8) {
     const int e = tc_debug_set_buffer(host_mapped_u64x8);
@@ -194,15 +204,39 @@ int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits
     const bool tc_ok = local_attn_bwd_tc_supported(C, k, dtype, flow_dtype, layout, grad_out, grad_source);
     if (algo == 2 && !tc_ok) return GFLA_E_NOTSUP;
     if (algo == 2 || (algo == 0 && tc_ok)) {
-        // grad_source: tile kernel (GEMM + TMA reduce-add); grad_flow / grad_logits: per-pixel dot products
-        if (!accumulate) cudaMemsetAsync(grad_source, 0, (size_t)B * C * Hs * Ws * elem_size(dtype), (cudaStream_t)stream);
-        int e = local_attn_bwd_gs_tc(flow, logits, grad_out, grad_source, B, C, Hs, Ws, H, W, k, (cudaStream_t)stream);
-        if (e != GFLA_OK) return e;
-        if (local_attn_bwd_q_tc_supported(C, k))
-            return local_attn_bwd_q_tc(source, flow, logits, grad_out, grad_flow, grad_logits, B, C, Hs, Ws, H, W, k,
-                                       accumulate, (cudaStream_t)stream);
-        return local_attn_bwd_gather(source, flow, logits, grad_out, grad_source, grad_flow, grad_logits, B, C, Hs, Ws, H,
-                                     W, k, dtype, flow_dtype, accumulate, layout, /*do_gs=*/0, (cudaStream_t)stream);
+        // grad_source: tile kernel (GEMM + TMA reduce-add); grad_flow / grad_logits: per-pixel dot products.
+        // The batch is walked in chunks of `cb` samples (zero-fill, grad_source kernel, grad_flow/logits kernel per chunk):
+        // with a chunk's grad_source + grad_out + source (3 * C*H*W*2 bytes per sample) inside the 126 MB L2, the zero-fill
+        // never reaches HBM before the reduce-adds land on it, and the second kernel finds grad_out still in L2.
+        const size_t per_s = (size_t)C * Hs * Ws * elem_size(dtype), per_o = (size_t)C * H * W * elem_size(dtype);
+        const size_t per_f = (size_t)2 * H * W * elem_size(flow_dtype), per_l = (size_t)k * k * H * W * elem_size(dtype);
+        int cb = B;
+        {
+            const char* v = getenv("GFLA_BWD_CHUNK");
+            if (v) cb = atoi(v) > 0 ? atoi(v) : B;
+        }
+        const bool q_tc = local_attn_bwd_q_tc_supported(C, k);
+        for (int b0 = 0; b0 < B; b0 += cb) {
+            const int nb = (B - b0 < cb) ? (B - b0) : cb;
+            const char* s_ = (const char*)source + b0 * per_s;
+            const char* f_ = (const char*)flow + b0 * per_f;
+            const char* l_ = (const char*)logits + b0 * per_l;
+            const char* g_ = (const char*)grad_out + b0 * per_o;
+            char* gs_ = (char*)grad_source + b0 * per_s;
+            char* gf_ = (char*)grad_flow + b0 * per_f;
+            char* gl_ = (char*)grad_logits + b0 * per_l;
+            int e = GFLA_OK;
+            if (!accumulate) e = zero_async(gs_, nb * per_s, (cudaStream_t)stream);
+            if (e == GFLA_OK) e = local_attn_bwd_gs_tc(f_, l_, g_, gs_, nb, C, Hs, Ws, H, W, k, (cudaStream_t)stream);
+            if (e != GFLA_OK) return e;
+            if (q_tc)
+                e = local_attn_bwd_q_tc(s_, f_, l_, g_, gf_, gl_, nb, C, Hs, Ws, H, W, k, accumulate, (cudaStream_t)stream);
+            else
+                e = local_attn_bwd_gather(s_, f_, l_, g_, gs_, gf_, gl_, nb, C, Hs, Ws, H, W, k, dtype, flow_dtype, accumulate,
+                                          layout, /*do_gs=*/0, (cudaStream_t)stream);
+            if (e != GFLA_OK) return e;
+        }
+        return GFLA_OK;
     }
     return local_attn_bwd_gather(source, flow, logits, grad_out, grad_source, grad_flow, grad_logits, B, C, Hs, Ws, H, W,
                                  k, dtype, flow_dtype, accumulate, layout, /*do_gs=*/1, (cudaStream_t)stream);

@@ -181,8 +181,9 @@ int block_extract_bwd(const void* src, const void* flow, const void* gout, void*
                       int Hs, int Ws, int Hf, int Wf, int k, int dtype, int flow_dtype, int gs_dtype, int accumulate,
                       cudaStream_t st_) {
     if (!accumulate) {
-        cudaMemsetAsync(gsrc, 0, (size_t)B * C * Hs * Ws * elem_size(gs_dtype), st_);
-        cudaMemsetAsync(gflow, 0, (size_t)B * 2 * Hf * Wf * elem_size(flow_dtype), st_);
+        int e = zero_async(gsrc, (size_t)B * C * Hs * Ws * elem_size(gs_dtype), st_);
+        if (e == GFLA_OK) e = zero_async(gflow, (size_t)B * 2 * Hf * Wf * elem_size(flow_dtype), st_);
+        if (e != GFLA_OK) return e;
     }
     return GFLA_DISPATCH_T(dtype, [&]() -> int {
         if (gs_dtype != dtype) {   // 16-bit data, fp32 grad_source buffer

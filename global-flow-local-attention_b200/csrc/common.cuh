@@ -95,8 +95,19 @@ inline int channel_splits(long long items, int C, int threads) {
     return s;
 }
 
+// Process-wide count of kernels this library has launched (statistics only: bench.py reports it as
+// `gpu_launches`; relaxed atomic, never read by the library itself).  Defined in api.cu.
+void count_launch();
+
 inline int launch_status() {
     cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) count_launch();
+    return e == cudaSuccess ? GFLA_OK : static_cast<int>(e);
+}
+
+// zero-fill on the caller's stream; the status is the caller's to propagate (nothing may be launched after a failure)
+inline int zero_async(void* p, size_t bytes, cudaStream_t st_) {
+    cudaError_t e = cudaMemsetAsync(p, 0, bytes, st_);
     return e == cudaSuccess ? GFLA_OK : static_cast<int>(e);
 }
 

@@ -346,7 +346,10 @@ int local_attn_bwd_gather(const void* src, const void* flow, const void* logits,
                           int flow_dtype, int accumulate, int layout, int do_gs, cudaStream_t st_) {
     // do_gs = 0: grad_source is produced elsewhere (tile kernel); only grad_flow / grad_logits here
     const int nhwc = layout == GFLA_NHWC;
-    if (!accumulate && do_gs) cudaMemsetAsync(gsrc, 0, (size_t)B * C * Hs * Ws * elem_size(dtype), st_);
+    if (!accumulate && do_gs) {
+        const int e = zero_async(gsrc, (size_t)B * C * Hs * Ws * elem_size(dtype), st_);
+        if (e != GFLA_OK) return e;
+    }
     return GFLA_DISPATCH_T(dtype, [&]() -> int {
         if (flow_dtype == dtype)
             return la_bwd_k<T, T>(src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, k, accumulate, nhwc, do_gs, st_);

@@ -311,7 +311,10 @@ int resample2d_fwd(const void* in1, const void* in2, void* out, int B, int C, in
 
 int resample2d_bwd(const void* in1, const void* in2, const void* gout, void* gin1, void* gin2, int B, int C, int Hi,
                    int Wi, int H, int W, int ks, int dil, int dtype, int accumulate, cudaStream_t st_) {
-    if (!accumulate) cudaMemsetAsync(gin1, 0, (size_t)B * C * Hi * Wi * elem_size(dtype), st_);
+    if (!accumulate) {
+        const int e = zero_async(gin1, (size_t)B * C * Hi * Wi * elem_size(dtype), st_);
+        if (e != GFLA_OK) return e;
+    }
     if (dtype == GFLA_F32) { GFLA_RS_DISPATCH(float, rs_launch_bwd, in1, in2, gout, gin1, gin2, B, C, Hi, Wi, H, W, dil, accumulate, st_) }
     if (dtype == GFLA_F64) { GFLA_RS_DISPATCH(double, rs_launch_bwd, in1, in2, gout, gin1, gin2, B, C, Hi, Wi, H, W, dil, accumulate, st_) }
     return GFLA_E_DTYPE;

@@ -38,8 +38,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Debug channel: a host-mapped (pinned) buffer of 8 x u64 set through gfla_debug_set_buffer(); survives a trap.
 static __device__ unsigned long long* g_tc_dbg = nullptr;
 
-// Bounded wait: a protocol bug must abort the kernel (trap -> launch error), never hang the GPU.
+// Bounded wait: a protocol bug must abort the kernel (trap -> launch error), never hang the GPU.  The bound is a
+// safety net, not a scheduling assumption: ~10 s of SM cycles by default (time-slicing, MPS preemption, a
+// debugger or compute-sanitizer can legitimately stretch a wait by orders of magnitude over the ~microseconds a
+// healthy pipeline needs); build with -DGFLA_TC_WAIT_CYCLES=<n> for a shorter fuse while developing a kernel.
 // `tag` identifies the waiter (role << 16 | barrier kind << 8 | slot) in the debug buffer.
+#ifndef GFLA_TC_WAIT_CYCLES
+#define GFLA_TC_WAIT_CYCLES 20000000000LL
+#endif
 static __device__ __noinline__ void mbar_timeout(uint32_t tag, uint32_t parity, uint32_t iter) {
     unsigned long long* d = g_tc_dbg;
     if (d != nullptr) {
@@ -83,7 +89,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
 #ifdef GFLA_TC_PROFILE
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {   // try_wait itself suspends the thread for a while before giving up
-        if (clock64() - t0 > 2000000000LL) mbar_timeout(tag, parity, iter);
+        if (clock64() - t0 > GFLA_TC_WAIT_CYCLES) mbar_timeout(tag, parity, iter);
     }
     const long long dt = clock64() - t0;
     if (dt > 64) tc_profile_add((tag >> 16) & 3, (tag >> 8) & 7, dt);
@@ -91,7 +97,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 2000000000LL) mbar_timeout(tag, parity, iter);  // ~1 s
+        if (clock64() - t0 > GFLA_TC_WAIT_CYCLES) mbar_timeout(tag, parity, iter);
     }
 #endif
 }

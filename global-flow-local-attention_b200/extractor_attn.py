@@ -43,7 +43,7 @@ class LocalAttnFunction(Function):
     @staticmethod
     def backward(ctx, grad_output):
         source, flow_field, logits = ctx.saved_tensors
-        gs, gf, gl = F_.local_attn_bwd(source, flow_field, logits, grad_output, ctx.kernel_size)
+        gs, gf, gl = F_.local_attn_bwd(source, flow_field, logits, grad_output, ctx.kernel_size, algo=ctx.algo)
         return gs, gf, gl, None, None
 
 
@@ -54,8 +54,19 @@ def _keep_format(t):
     return t.contiguous()
 
 
+def _flow_f32(source, flow_field):
+    """16-bit feature tensors pair with an fp32 flow: the tap indices are then bit-identical to the fp32
+    reference (block_extractor_kernel.cu:62-76) and the tcgen05 tile kernels -- which take fp32 flow only --
+    serve the call.  A bf16/f16 flow (e.g. from a network cast wholesale with .bfloat16()) is widened here;
+    autograd casts its gradient back to the flow's dtype."""
+    if source.dtype in (torch.bfloat16, torch.float16) and flow_field.dtype != torch.float32:
+        return flow_field.float()
+    return flow_field
+
+
 def local_attention(source, flow_field, logits, kernel_size, algo="auto"):
-    return LocalAttnFunction.apply(_keep_format(source), flow_field.contiguous(), logits.contiguous(), kernel_size, algo)
+    return LocalAttnFunction.apply(_keep_format(source), _flow_f32(source, flow_field).contiguous(), logits.contiguous(),
+                                   kernel_size, algo)
 
 
 class ExtractorAttn(nn.Module):
@@ -109,7 +120,7 @@ class ExtractorAttn(nn.Module):
                 return target * (1 - mask) + out_attn * mask
             src = _keep_format(source)
             fmt = torch.channels_last if (not src.is_contiguous()) else torch.contiguous_format
-            return F_.local_attn_blend_fwd(src, flow_field.contiguous(), logits.contiguous(),
+            return F_.local_attn_blend_fwd(src, _flow_f32(src, flow_field).contiguous(), logits.contiguous(),
                                            target.contiguous(memory_format=fmt), mask.to(source.dtype), self.kernel_size)
         assert mask is None, "mask blend is only fused for the softmax variant"
         # softmax=None in the reference means "apply the nonlinearity instead": keep the literal composition
@@ -119,7 +130,7 @@ class ExtractorAttn(nn.Module):
     def hook_attn_param(self, source, target, flow_field):
         logits, block_source = self._logits(source, target, flow_field)
         if self.fused_softmax:
-            result, probs = F_.local_attn_fwd(_keep_format(source), flow_field.contiguous(), logits.contiguous(),
+            result, probs = F_.local_attn_fwd(_keep_format(source), _flow_f32(source, flow_field).contiguous(), logits.contiguous(),
                                               self.kernel_size, return_probs=True)
             return probs, result
         attn_param_ = self.fully_connect_layer[-1](logits)

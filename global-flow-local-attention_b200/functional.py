@@ -233,7 +233,8 @@ def local_attn_bwd(source, flow, logits, grad_out, k, algo="auto"):
     layout = _feature_layout(source)
     assert flow.is_contiguous() and logits.is_contiguous()
     _need_cuda(source, flow, logits, grad_out)
-    if layout == _lib.GFLA_NCHW and algo == "auto" and _tile_bwd_eligible(source, flow, k):
+    if (layout == _lib.GFLA_NCHW and algo == "auto" and _tile_bwd_eligible(source, flow, k)
+            and not source.is_contiguous(memory_format=torch.channels_last)):   # H=W=1 / C=1: both formats at once
         # The backward tile kernels are channels-last only (every operand must be channel-contiguous for TMA).
         # For planar callers, re-lay the two feature tensors (two extra passes over them) instead of falling
         # back to the scalar-atomics kernel: ~100x faster at cfg2.

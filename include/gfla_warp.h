@@ -76,6 +76,11 @@ int gfla_device_check(void);
  * traps instead of hanging the GPU.  Not used on the normal path. */
 int gfla_debug_set_buffer(void* host_mapped_u64x8);
 
+/* Statistics: number of kernels this library has launched in this process so far (all entry points, all
+ * threads; a relaxed counter that nothing inside the library reads).  bench.py reports the difference across
+ * its timed region as `gpu_launches`. */
+unsigned long long gfla_debug_launch_count(void);
+
 /* Debug aid for tuning the forward tile kernels: cycles their warps spent blocked on the pipeline barriers.
  * Only in profile builds of the library (GFLA_BUILD_PROFILE=1 at build time, -DGFLA_TC_PROFILE); a normal build
  * carries no timing code and returns GFLA_E_NOTSUP.  `which`: 0 = per-tile kernel, 1 = strip kernel.  Copies the

@@ -525,7 +525,7 @@ def test_local_attn_bwd_tile_vs_oracle(F_, oracle_lib, shape, kind):
     assert gs.is_contiguous(memory_format=torch.channels_last)
     ogs, ogf, ogl = oracle_lib.local_attn_bwd(host(s), f.cpu().numpy(), host(l), host(g), k)
     scale = max(1.0, float(np.abs(ogs).max()))
-    np.testing.assert_allclose(host(gs), ogs, rtol=0, atol=1e-2 * scale)      # bf16 storage + bf16 reduce-adds
+    np.testing.assert_allclose(host(gs), ogs, rtol=0, atol=1e-2)              # flat (north_star): bf16 storage + bf16 reduce-adds
     np.testing.assert_allclose(host(gl), ogl, rtol=0, atol=1e-2)
     np.testing.assert_allclose(host(gf), ogf, rtol=2e-2, atol=2e-2 * max(1.0, float(np.abs(ogf).max())))
 
@@ -542,7 +542,10 @@ def test_local_attn_bwd_tile_irregular_taps(F_, oracle_lib):
     l = torch.from_numpy(rng.standard_normal((B, k * k, H, W)).astype(np.float32)).to(DEV).bfloat16()
     gs, gf, gl = F_.local_attn_bwd(s, torch.from_numpy(flow).to(DEV), l, g, k, algo="tile")
     ogs, ogf, ogl = oracle_lib.local_attn_bwd(host(s), flow, host(l), host(g), k)
-    np.testing.assert_allclose(host(gs), ogs, rtol=0, atol=1e-2 * max(1.0, float(np.abs(ogs).max())))
+    np.testing.assert_allclose(host(gs), ogs, rtol=0, atol=1e-2)
+    # the irregular pixels' grad_flow / grad_logits come from the literal 4-tap path of the same kernel
+    np.testing.assert_allclose(host(gl), ogl, rtol=0, atol=1e-2)
+    np.testing.assert_allclose(host(gf), ogf, rtol=2e-2, atol=2e-2 * max(1.0, float(np.abs(ogf).max())))
 
 
 def test_local_attn_bwd_nchw_bf16_routes_through_tile_kernels(F_, oracle_lib):
