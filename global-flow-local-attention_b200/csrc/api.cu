@@ -24,6 +24,7 @@ int tc_debug_set_buffer(void*);
 int tc_debug_set_buffer_bwd(void*);
 int tc_wait_profile_fwd(int, unsigned long long*);
 int tc_wait_profile_strip(int, unsigned long long*);
+int tc_wait_profile_bwd_fused(int, unsigned long long*);
 bool local_attn_fwd_tc_supported(int B, int C, int Hs, int Ws, int H, int W, int k, int dtype, int flow_dtype, int layout, const void* src, const void* out);
 }  // namespace gfla
 
@@ -36,6 +37,9 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace gfla
 
 using namespace gfla;
+
+// which backward the automatic path takes where both can serve the call (GFLA_BWD_FUSED=0/1 overrides)
+constexpr bool kBwdFusedDefault = false;
 
 #define REQ_PTR(p) do { if ((p) == nullptr) return GFLA_E_NULL; } while (0)
 #define REQ_ALIGN(p, dt) do { if (!aligned((p), elem_size(dt))) return GFLA_E_ALIGN; } while (0)
@@ -68,11 +72,12 @@ int gfla_device_check(void) {
     return (major == 10 && minor == 0) ? GFLA_OK : static_cast<int>(cudaErrorNoKernelImageForDevice);
 }
 
-int gfla_debug_wait_profile(int which, int enable, unsigned long long* out_u64x32) {
-    if (which != 0 && which != 1) return GFLA_E_SHAPE;
+int gfla_debug_wait_profile(int which, int enable, unsigned long long* out_u64x64) {
+    if (which < 0 || which > 2) return GFLA_E_SHAPE;
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return static_cast<int>(e);
-    return which == 0 ? tc_wait_profile_fwd(enable, out_u64x32) : tc_wait_profile_strip(enable, out_u64x32);
+    if (which == 2) return tc_wait_profile_bwd_fused(enable, out_u64x64);
+    return which == 0 ? tc_wait_profile_fwd(enable, out_u64x64) : tc_wait_profile_strip(enable, out_u64x64);
 }
 
 unsigned long long gfla_debug_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
@@ -219,10 +224,10 @@ int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits
         }
         const bool q_tc = local_attn_bwd_q_tc_supported(C, k);
         // one fused kernel (grad_out tile read once) where it can serve the shape; GFLA_BWD_FUSED=0 keeps the two-kernel path
-        bool fused = local_attn_bwd_fused_supported(C, k, source);
+        bool fused = kBwdFusedDefault && local_attn_bwd_fused_supported(C, k, source);
         {
             const char* v = getenv("GFLA_BWD_FUSED");
-            if (v && atoi(v) == 0) fused = false;
+            if (v) fused = atoi(v) != 0 && local_attn_bwd_fused_supported(C, k, source);
         }
         for (int b0 = 0; b0 < B; b0 += cb) {
             const int nb = (B - b0 < cb) ? (B - b0) : cb;

@@ -116,6 +116,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_TMEM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t_start = tc_profile_clock();
     const int gxn = (W + GW - 1) / GW, gyn = (H + GH - 1) / GH;
     const int ngroups = B * gyn * gxn;
     const long long hw = (long long)H * W;
@@ -278,6 +279,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             const int px = gx0 + (m & 15), py = gy0 + (m >> 4);
             const bool valid = px < W && py < H;
             const long long pofs = (long long)py * W + px;
+            const long long tp0 = tc_profile_clock();
             float p[KK];
             float fx = 0.f, fy = 0.f;
             bool regular = false;
@@ -295,6 +297,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             }
             if (g + (int)gridDim.x < ngroups) load_pixel(g + gridDim.x);
             const bool live = valid && regular;
+            tc_profile_add(2, 6, tc_profile_clock() - tp0);          // softmax / taps of this group, raw loads of the next
             float Qw[K1 * K1];  // Q at the (clamped) window positions
 #pragma unroll
             for (int i = 0; i < K1 * K1; ++i) Qw[i] = 0.f;
@@ -348,6 +351,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 }
             }
             // ---- finalize this pixel
+            const long long tq0 = tc_profile_clock();
             float dp[KK];
             float gfx = 0.f, gfy = 0.f;
             if (live) {
@@ -422,6 +426,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 gf[0] = accumulate ? gf[0] + gfx : gfx;
                 gf[hw] = accumulate ? gf[hw] + gfy : gfy;
             }
+            tc_profile_add(2, 7, tc_profile_clock() - tq0);          // softmax backward, d/dflow, stores
         }
     } else if (warp < 12) {
         // ================================================================= slab builders (thread = pixel)
@@ -453,6 +458,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             const bool valid = px < W && py < H;
             int X0 = 0, Y0 = 0;
             bool live = false;
+            const long long tw0 = tc_profile_clock();
             if (valid) {
                 float p[KK];
 #pragma unroll
@@ -467,6 +473,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 }
             }
             if (g + (int)gridDim.x < ngroups) load_pixel(g + gridDim.x);
+            tc_profile_add(3, 6, tc_profile_clock() - tw0);          // window of this group, raw loads of the next
             mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x030500, gi);
             const GroupInfo inf = infos[gi % FB_NINFO];
             const int nb4 = (inf.nrc + 1) / 2;
@@ -596,6 +603,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+    tc_profile_total(t_start);
 }
 
 template <int K, int CN>
@@ -635,6 +643,8 @@ static int launch_fused(const void* src, const void* flow, const void* logits, c
 }
 
 }  // namespace tc
+
+int tc_wait_profile_bwd_fused(int enable, unsigned long long* out64) { return tc::tc_wait_profile(enable, out64); }
 
 bool local_attn_bwd_fused_supported(int C, int k, const void* src) {
     return (C == 64 || C == 128 || C == 256) && (k == 3 || k == 5) && aligned(src, 16);

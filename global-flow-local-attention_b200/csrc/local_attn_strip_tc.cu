@@ -9,14 +9,18 @@
 // sits in shared memory (two weight slabs, one B operand), so in steady state a tile fetches only the
 // ~8 rows its predecessor did not already see.  The schedule is in strip_plan.h.
 //
-// Warp roles (10 warps, persistent CTA, static round-robin over strips):
-//   warp 0      producer: tile bounding boxes, step schedule, TMA row loads;
-//   warp 1      MMA issuer: per step one MMA set per consuming tile (accumulators alternate between the
-//               two TMEM halves; the next tile's half is claimed at its first shared step);
-//   warps 2-5   builders: softmax + tap arithmetic + window collapse for the current AND the next tile,
-//               one weight slab per (step, consuming tile);
-//   warps 6-9   epilogue: TMEM -> bf16 -> 64-byte channels-last stores (optional mask blend), literal
-//               4-tap recomputation of the irregular pixels (bit-identical indexing).
+// Warp roles (4 warpgroups = 16 warps, persistent CTA, static round-robin over strips; setmaxnreg moves the control
+// warpgroup's registers to the builders and the epilogue):
+//   warp 0        producer: tile bounding boxes, step schedule, TMA row loads;
+//   warp 1        MMA issuer: per step one MMA set per consuming tile (accumulators alternate between the
+//                 two TMEM halves; the next tile's half is claimed at its first shared step);   (warps 2, 3 idle)
+//   warps 4-7     builder team 0, warps 8-11 builder team 1 (thread = pixel): team T owns the tiles of parity T --
+//                 softmax + tap arithmetic + window collapse once per tile, then that tile's weight slab (sub-slab T
+//                 of the stage) in every step that feeds it: the shared steps of the previous tile's pass and the
+//                 steps of its own pass.  While one team fills, the other builds its next window: the per-pixel
+//                 work, which bounded the 4-builder-warp version, runs two tiles deep;
+//   warps 12-15   epilogue: TMEM -> bf16 -> swizzled staging -> TMA tensor store (optional mask blend), literal
+//                 4-tap recomputation of the irregular pixels (bit-identical indexing).
 #include "strip_plan.h"
 #include "tile_window.cuh"
 
@@ -28,7 +32,11 @@ constexpr int ST_RCH = 2;        // source rows per step (fixed by strip_plan.h:
 constexpr int ST_FBW = 32;       // source positions per row segment
 constexpr int ST_NINFO = 8;      // >= stages + 3: every tile pass has at least one step (strip_plan), so the
                                  // producer is never more than `stages` tiles ahead of the builders / MMA warp
-constexpr int ST_THREADS = 320;
+constexpr int ST_THREADS = 512;
+constexpr int ST_REG_CTRL = 72, ST_REG_BUILD = 152, ST_REG_EPI = 136;   // per-thread registers by warpgroup; sum over the 4 groups = 512
+static_assert(ST_REG_CTRL + 2 * ST_REG_BUILD + ST_REG_EPI <= 512, "register budget");
+template <int N> __device__ __forceinline__ void st_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void st_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 template <int CN>
 struct StripSmem {
@@ -37,7 +45,7 @@ struct StripSmem {
     static constexpr int FA_SLAB = 128 * ST_FBW * 2;           // weight slab: [128 pixels][32 positions] bf16
     static constexpr int S_STAGE = ST_RCH * S_SLAB;
     static constexpr int A_TILE = ST_RCH * FA_SLAB;            // the slabs of one consuming tile
-    static constexpr int A_STAGE = 2 * A_TILE;                 // current tile, next tile
+    static constexpr int A_STAGE = 2 * A_TILE;                 // sub-slab 0: tiles of even parity (team 0), sub-slab 1: odd (team 1)
     static constexpr int W_TILE = 36 * 128 * 2;                // collapsed windows of one tile, [18 words][128 pixels]
     static constexpr int OFF_S = 0;
     static constexpr int OFF_A = OFF_S + NSTAGE * S_STAGE;
@@ -46,7 +54,7 @@ struct StripSmem {
     static constexpr int OFF_O = OFF_W + 2 * W_TILE;           // 64B-swizzled: 512-byte aligned
     static constexpr int OFF_INFO = OFF_O + 4 * O_WARP;
     static constexpr int OFF_BAR = OFF_INFO + ST_NINFO * 32;
-    static constexpr int NBAR = 3 * NSTAGE + 4 + ST_NINFO;
+    static constexpr int NBAR = 4 * NSTAGE + 4 + ST_NINFO;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int TOTAL = OFF_TMEM + 16;
     static constexpr int ALLOC = TOTAL + 1024;                 // slack to align the base to 1024 B
@@ -108,11 +116,11 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
     uint64_t* full_s = bars;                      // [NSTAGE] TMA bytes landed
-    uint64_t* full_a = bars + NSTAGE;             // [NSTAGE] 128 builder arrivals
-    uint64_t* empty = bars + 2 * NSTAGE;          // [NSTAGE] MMAs of the stage retired
-    uint64_t* acc_full = bars + 3 * NSTAGE;       // [2]
-    uint64_t* acc_empty = bars + 3 * NSTAGE + 2;  // [2]
-    uint64_t* info_full = bars + 3 * NSTAGE + 4;  // [ST_NINFO]
+    uint64_t* full_a = bars + NSTAGE;             // [2][NSTAGE] 128 arrivals of builder team T: sub-slab T of the stage is written
+    uint64_t* empty = bars + 3 * NSTAGE;          // [NSTAGE] MMAs of the stage retired
+    uint64_t* acc_full = bars + 4 * NSTAGE;       // [2]
+    uint64_t* acc_empty = bars + 4 * NSTAGE + 2;  // [2]
+    uint64_t* info_full = bars + 4 * NSTAGE + 4;  // [ST_NINFO]
     StripTile* infos = reinterpret_cast<StripTile*>(smem + SM::OFF_INFO);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_TMEM);
 
@@ -128,7 +136,9 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
     const long long hw = (long long)H * W;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full_s[i], 1); mbar_init(&full_a[i], 128); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < NSTAGE; ++i) {
+            mbar_init(&full_s[i], 1); mbar_init(&full_a[i], 128); mbar_init(&full_a[NSTAGE + i], 128); mbar_init(&empty[i], 1);
+        }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         for (int i = 0; i < ST_NINFO; ++i) mbar_init(&info_full[i], 1);
         fence_barrier_init();
@@ -145,7 +155,9 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
     first.start(geo, blockIdx.x);
     const int ustride = gridDim.x;
 
-    if (warp == 0) {
+    if (warp < 4) {
+      st_reg_dec<ST_REG_CTRL>();
+      if (warp == 0) {
         // ================================================================= producer
         // The flow of a tile is loaded a whole pass before its bounding box is needed (TileFlow registers in flight
         // across the TMA loop): a box costs ~4 us of load latency, which otherwise stalls the row loads once per tile.
@@ -218,10 +230,11 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
             }
             tc_profile_add(0, 6, tc_profile_clock() - tb0);          // box of tile n+2, flow loads of tile n+3
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         // ================================================================= MMA issuer
         constexpr uint32_t idesc = make_idesc_f16(128, CN, true, false, true);
         uint32_t it = 0;
+        uint32_t par_a[2] = {0u, 0u};   // per builder team: phase parity of full_a[team][slot], one bit per slot
         int ti = 0;
         bool started = false;   // this tile's accumulator already holds the previous pass's shared steps
         for (TileIt cur = first; cur.ok(geo); cur.next(geo, ustride), ++ti) {
@@ -244,7 +257,12 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
                     const int slot = it % NSTAGE;
                     const uint32_t par = (it / NSTAGE) & 1;
                     mbar_wait(&full_s[slot], par, 0x010000 | slot, it);
-                    mbar_wait(&full_a[slot], par, 0x010100 | slot, it);
+                    mbar_wait(&full_a[buf * NSTAGE + slot], (par_a[buf] >> slot) & 1u, 0x010100 | slot, it);   // this tile's slab
+                    par_a[buf] ^= 1u << slot;
+                    if (shared) {                                                                              // the next tile's slab
+                        mbar_wait(&full_a[(buf ^ 1) * NSTAGE + slot], (par_a[buf ^ 1] >> slot) & 1u, 0x010700 | slot, it);
+                        par_a[buf ^ 1] ^= 1u << slot;
+                    }
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t a0 = smem_u32(smem + SM::OFF_A + slot * SM::A_STAGE);
@@ -252,14 +270,15 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
 #pragma unroll
                         for (int sub = 0; sub < 2; ++sub) {
                             if ((sub == 1 && !shared) || (knobs & 4096)) break;
-                            const uint32_t d_tmem = tmem_base + (sub == 0 ? buf : (buf ^ 1)) * CN;
+                            const int par_t = sub == 0 ? buf : (buf ^ 1);      // parity of the consuming tile = its TMEM half = its sub-slab
+                            const uint32_t d_tmem = tmem_base + par_t * CN;
                             const bool fresh = sub == 0 ? !started : !next_started;
 #pragma unroll
                             for (int rr = 0; rr < RCH; ++rr)
 #pragma unroll
                                 for (int h = 0; h < FBW / 16; ++h) {  // K = 16 positions per MMA
                                     // A = [128 px][32 pos], K-major, 64B rows, 64B swizzle; K-advance = +32 B
-                                    const uint64_t ad = make_smem_desc(a0 + sub * SM::A_TILE + rr * SM::FA_SLAB + h * 32, 16, 512, kSwizzle64);
+                                    const uint64_t ad = make_smem_desc(a0 + par_t * SM::A_TILE + rr * SM::FA_SLAB + h * 32, 16, 512, kSwizzle64);
                                     // B = [32 x][64 ch] per channel group, MN-major, 128B swizzle: LBO = next channel group,
                                     // SBO = next 8 positions (1 KB); K-advance = 2 KB
                                     const uint64_t bd = make_smem_desc(b0 + rr * SM::S_SLAB + h * 2048, FBW * 128, 1024, kSwizzle128);
@@ -277,17 +296,21 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
             __syncwarp();
             started = next_started;   // false after the last tile of a strip (it never shares)
         }
-    } else if (warp < 6) {
-        // ================================================================= builders
+      }   // warps 2, 3: no role (they pad the control warpgroup so that setmaxnreg can hand their registers on)
+    } else if (warp < 12) {
+        // ================================================================= builders, team T = tiles of parity T
+        st_reg_inc<ST_REG_BUILD>();
+        const int T = (warp - 4) >> 2;
         const int q = warp & 3, m = q * 32 + lane;  // pixel index inside a tile
         const float inv_kk = 1.0f / static_cast<float>(KK);
-        const uint32_t wsm_base = smem_u32(smem + SM::OFF_W) + m * 4;           // + (tile parity) * W_TILE
-        const uint32_t a_base = smem_u32(smem + SM::OFF_A) + m * (FBW * 2);     // this pixel's row in slab 0
+        const uint32_t wsm_a = smem_u32(smem + SM::OFF_W) + T * SM::W_TILE + m * 4;                 // this team's window words
+        const uint32_t a_base = smem_u32(smem + SM::OFF_A) + T * SM::A_TILE + m * (FBW * 2);        // this pixel's row in sub-slab T of stage 0
         const uint32_t swz = ((m >> 1) & 3) << 4;                               // 64B-swizzle XOR of this row's 16B chunks
+        uint64_t* my_full = full_a + T * NSTAGE;
         uint32_t it = 0, dirty = 0xffffffffu;   // slab rows start with unknown contents: treat them as dirty
         int ti = 0;
-        // Raw inputs of this thread's pixel of one tile.  Like the producer's flow, they are loaded one pass before the
-        // window is built from them, so their latency hides behind the slab fills of the current tile.
+        // Raw inputs of this thread's pixel of the team's NEXT tile: loaded a whole tile pass before the window is built
+        // from them, so their latency hides behind the fills.
         __nv_bfloat16 lg[KK];
         float pfx = 0.f, pfy = 0.f;
         auto load_pixel = [&](const TileIt& tl) {
@@ -302,7 +325,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
             }
         };
         // collapsed window of that pixel -> shared memory; returns whether the pixel exists and is regular
-        auto make_window = [&](const TileIt& tl, uint32_t wsm_a, int& X0, int& Y0) -> bool {
+        auto make_window = [&](const TileIt& tl, int& X0, int& Y0) -> bool {
             const int px = tl.gx * GW + (m & 15), py = tl.ty * GH + (m >> 4);
             X0 = 0; Y0 = 0;
             if (!(px < W && py < H)) return false;
@@ -323,70 +346,80 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
             store_window_words<K>(wsm_a, w);
             return true;
         };
-        TileIt ld = first, pend_it = first;
-        int X0 = 0, Y0 = 0, nX0 = 0, nY0 = 0;
-        bool live = false, nlive = false, pend = false;
+        // `mine` walks this team's tiles (parity T of the CTA's tile sequence), `ld` one own tile further (raw-input prefetch)
+        TileIt mine = first, ld = first;
+        if (T == 1 && mine.ok(geo)) mine.next(geo, ustride);
+        ld = mine;
+        int X0 = 0, Y0 = 0;
+        bool live = false, have = false;          // window of tile `mine` is in shared memory / registers
         if (ld.ok(geo)) {
             load_pixel(ld);
-            live = make_window(ld, wsm_base, X0, Y0);
             ld.next(geo, ustride);
+            if (ld.ok(geo)) ld.next(geo, ustride);
         }
-        if (ld.ok(geo)) {
-            load_pixel(ld);
-            pend_it = ld;
-            pend = true;
-            ld.next(geo, ustride);
+        if (T == 0 && mine.ok(geo)) {             // the CTA's first tile has no previous pass to hide its window behind
+            live = make_window(mine, X0, Y0);
+            have = true;
+            if (ld.ok(geo)) {
+                load_pixel(ld);
+                ld.next(geo, ustride);
+                if (ld.ok(geo)) ld.next(geo, ustride);
+            }
         }
         for (TileIt cur = first; cur.ok(geo); cur.next(geo, ustride), ++ti) {
-            const uint32_t wsm_cur = wsm_base + (ti & 1) * SM::W_TILE, wsm_nxt = wsm_base + ((ti + 1) & 1) * SM::W_TILE;
-            const long long tw0 = tc_profile_clock();
-            const bool have_n = pend;             // this CTA's next tile (same strip or not): its window is built now
-            if (pend) nlive = make_window(pend_it, wsm_nxt, nX0, nY0);
-            pend = ld.ok(geo);
-            if (pend) {
-                load_pixel(ld);
-                pend_it = ld;
-                ld.next(geo, ustride);
+            const bool own = (ti & 1) == T;
+            if (!own && !have && mine.ok(geo)) {
+                // the other team's pass: this team's tile is the NEXT one -- build its window now (the other team is filling)
+                const long long tw0 = tc_profile_clock();
+                live = make_window(mine, X0, Y0);
+                have = true;
+                if (ld.ok(geo)) {
+                    load_pixel(ld);
+                    ld.next(geo, ustride);
+                    if (ld.ok(geo)) ld.next(geo, ustride);
+                }
+                tc_profile_add(2, 6, tc_profile_clock() - tw0);          // window of the team's next tile, loads of the one after
             }
-            tc_profile_add(2, 6, tc_profile_clock() - tw0);          // window of tile n+1, loads of tile n+2
             mbar_wait(&info_full[ti % ST_NINFO], (ti / ST_NINFO) & 1, 0x020500, ti);
             const StripTile t = infos[ti % ST_NINFO];
             long long fill_cycles = 0;
             for (int cb = 0; cb < t.ncb; ++cb) {
-                const int e0 = X0 - (t.xs + cb * FBW), e0n = nX0 - (t.xs + cb * FBW);   // box position of window column 0
-                const bool cols_hit = live && e0 > -K1 && e0 < FBW && !(knobs & 1024);
-                const bool cols_hit_n = have_n && nlive && e0n > -K1 && e0n < FBW && !(knobs & 1024);
+                const int e0 = X0 - (t.xs + cb * FBW);                                   // box position of window column 0
+                const bool cols_hit = have && live && e0 > -K1 && e0 < FBW && !(knobs & 1024);
                 for (int j = t.j0; j <= t.j1; ++j) {
                     if (strip_skipped(t, j)) continue;
+                    // Every step waits for its stage to be free, also the steps this team does not fill: a team that merely counted
+                    // steps could run phases ahead of the MMA warp, and a parity wait two phases early passes on the wrong phase.
                     const int slot = it % NSTAGE;
                     mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x020200 | slot, it);
-                    const long long tf0 = tc_profile_clock();
-                    const uint32_t a_stage = a_base + slot * SM::A_STAGE;
-                    const int R0 = 2 * j;
-                    bool wrote = false;
-                    if (!(knobs & 2048)) {
+                    if (own || strip_shared(t, j)) {        // this step feeds the team's tile: as the pass owner, or as the next tile of a shared step
+                        const long long tf0 = tc_profile_clock();
+                        const uint32_t a_stage = a_base + slot * SM::A_STAGE;
+                        const int R0 = 2 * j;
+                        bool wrote = false;
+                        if (!(knobs & 2048)) {
 #pragma unroll
-                    for (int rr = 0; rr < RCH; ++rr)
-                        wrote |= fill_slab_row<K, FBW>(a_stage + rr * SM::FA_SLAB, swz, wsm_cur, cols_hit, (R0 + rr) - Y0, e0, dirty,
-                                                  1u << ((slot * RCH + rr) * 2));
+                            for (int rr = 0; rr < RCH; ++rr)
+                                wrote |= fill_slab_row<K, FBW>(a_stage + rr * SM::FA_SLAB, swz, wsm_a, cols_hit, (R0 + rr) - Y0, e0, dirty,
+                                                               1u << (slot * RCH + rr));
+                        }
+                        if (wrote) fence_proxy_async_smem();
+                        mbar_arrive(&my_full[slot]);
+                        fill_cycles += tc_profile_clock() - tf0;
                     }
-                    if (strip_shared(t, j) && !(knobs & 2048)) {   // only inside a strip: the next tile is the one whose window was just built
-#pragma unroll
-                        for (int rr = 0; rr < RCH; ++rr)
-                            wrote |= fill_slab_row<K, FBW>(a_stage + SM::A_TILE + rr * SM::FA_SLAB, swz, wsm_nxt, cols_hit_n,
-                                                      (R0 + rr) - nY0, e0n, dirty, 1u << ((slot * RCH + rr) * 2 + 1));
-                    }
-                    if (wrote) fence_proxy_async_smem();
-                    mbar_arrive(&full_a[slot]);
-                    fill_cycles += tc_profile_clock() - tf0;
                     ++it;
                 }
             }
             tc_profile_add(2, 7, fill_cycles);              // slab fills
-            X0 = nX0; Y0 = nY0; live = nlive;
+            if (own) {                                      // this team's tile is finished: move on to its next one
+                have = false;
+                mine.next(geo, ustride);
+                if (mine.ok(geo)) mine.next(geo, ustride);
+            }
         }
     } else {
         // ================================================================= epilogue
+        st_reg_inc<ST_REG_EPI>();
         const int q = warp & 3, m = q * 32 + lane;
         int ti = 0;
         {
@@ -417,16 +450,8 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
                 // irregular pixels (zero weights -> zeros here) are overwritten below.
                 const uint32_t ob = smem_u32(smem + SM::OFF_O) + q * SM::O_WARP;
                 const uint32_t orow = ob + lane * 64, oswz = (lane >> 1) & 3;
-#pragma unroll 1
-                for (int cc = 0; cc < CN / 32; ++cc) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(taddr + cc * 32, v);
-                    tmem_ld_wait();
-                    if (cc == CN / 32 - 1) {   // accumulator fully read: hand it back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&acc_empty[buf]);
-                    }
+                // one 32-channel slice: (blend) -> bf16 -> swizzled staging -> TMA store
+                auto emit = [&](uint32_t (&v)[32], int cc) {
                     if (pv != nullptr) {   // blend in fp32 before the single rounding to bf16
                         const uint4* p4 = reinterpret_cast<const uint4*>(pv + cc * 32);
 #pragma unroll
@@ -459,6 +484,28 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
                         tma_store_4d(&tmap_out, ob, c0 + cc * 32, gx * GW, ty * GH + 2 * q, b);
                         bulk_commit();
                     }
+                };
+                // TMEM loads run one slice ahead of the conversion / store of the previous one (two register sets)
+                auto release_acc = [&]() {   // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                };
+                {
+                    constexpr int NCC = CN / 32;
+                    static_assert(NCC % 2 == 0, "channel slices are processed in pairs");
+                    uint32_t va[32], vb[32];
+                    tmem_ld_32x32(taddr, va);
+#pragma unroll 1
+                    for (int cc = 0; cc < NCC; cc += 2) {
+                        tmem_ld_wait();
+                        tmem_ld_32x32(taddr + (cc + 1) * 32, vb);
+                        emit(va, cc);
+                        tmem_ld_wait();
+                        if (cc + 2 < NCC) tmem_ld_32x32(taddr + (cc + 2) * 32, va);
+                        else release_acc();
+                        emit(vb, cc + 1);
+                    }
                 }
                 tc_profile_add(3, 6, tc_profile_clock() - te0);          // TMEM -> registers -> staging -> TMA store
                 // irregular pixels (fp32 rounding of (flow+offset)+coord straddling an integer, ~1e-5 of all pixels): the
@@ -478,7 +525,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
             }
         }
     }
-    if (warp >= 6 && lane == 0) bulk_wait_read<0>();   // staging buffers stay valid until their last store has read them
+    if (warp >= 12 && lane == 0) bulk_wait_read<0>();   // staging buffers stay valid until their last store has read them
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 2 * CN >= 32 ? 2 * CN : 32);

@@ -58,19 +58,19 @@ static __device__ __noinline__ void mbar_timeout(uint32_t tag, uint32_t parity, 
 }
 // Wait profile (debug builds only: GFLA_BUILD_PROFILE=1 python build.py, i.e. -DGFLA_TC_PROFILE): cycles that
 // lane 0 of every warp spent blocked, per (role, barrier kind) of the tag, plus explicit region timers (kinds 6, 7);
-// slot 7 of role 0 = total kernel cycles summed over the CTAs.  Read through gfla_debug_wait_profile().
+// slot 7 of role 0 = total kernel cycles summed over the CTAs.  8 roles x 8 kinds = 64 counters.  Read through gfla_debug_wait_profile().
 #ifdef GFLA_TC_PROFILE
-static __device__ unsigned long long g_tc_prof[32];
+static __device__ unsigned long long g_tc_prof[64];
 static __device__ int g_tc_prof_on = 0;
 __device__ __forceinline__ void tc_profile_add(int role, int kind, long long cycles) {   // call from every lane or lane 0
     if (g_tc_prof_on && (threadIdx.x & 31) == 0) atomicAdd(&g_tc_prof[role * 8 + kind], static_cast<unsigned long long>(cycles));
 }
 __device__ __forceinline__ long long tc_profile_clock() { return clock64(); }
-inline int tc_wait_profile(int enable, unsigned long long* out32) {
+inline int tc_wait_profile(int enable, unsigned long long* out64) {
     cudaError_t e = cudaSuccess;
-    if (out32 != nullptr) e = cudaMemcpyFromSymbol(out32, g_tc_prof, sizeof(unsigned long long) * 32);
+    if (out64 != nullptr) e = cudaMemcpyFromSymbol(out64, g_tc_prof, sizeof(unsigned long long) * 64);
     if (e == cudaSuccess) {
-        const unsigned long long zero[32] = {};
+        const unsigned long long zero[64] = {};
         e = cudaMemcpyToSymbol(g_tc_prof, zero, sizeof(zero));
     }
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_tc_prof_on, &enable, sizeof(int));
@@ -92,7 +92,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
         if (clock64() - t0 > GFLA_TC_WAIT_CYCLES) mbar_timeout(tag, parity, iter);
     }
     const long long dt = clock64() - t0;
-    if (dt > 64) tc_profile_add((tag >> 16) & 3, (tag >> 8) & 7, dt);
+    if (dt > 64) tc_profile_add((tag >> 16) & 7, (tag >> 8) & 7, dt);
 #else
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();

@@ -222,7 +222,8 @@ __device__ __forceinline__ bool fill_slab_row(uint32_t row, uint32_t swz, uint32
 // One "irregular" pixel (taps not consecutive integers: fp32 rounding of (flow+offset)+coord straddling an integer,
 // ~1e-5 of all pixels) with the reference's literal 4-taps-per-(i,j) arithmetic (block_extractor_kernel.cu:57-82
 // followed by base_function.py:804-810).  One such pixel costs 4*k*k*CN dependent loads, so a whole warp shares it:
-// every lane evaluates the (identical) softmax and taps, lanes split the channels [c0, c0 + CN).
+// every lane evaluates the (identical) softmax and taps, lanes split the channels [c0, c0 + CN).  The (i, j) loops stay
+// rolled: an unrolled tap table is register-hungry and would raise the pressure of (or spill into) the hot epilogue loop.
 template <int K, bool NHWC>
 __device__ __forceinline__ void irregular_pixel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ logits,
                                                 __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ prev,
@@ -232,12 +233,6 @@ __device__ __forceinline__ void irregular_pixel(const __nv_bfloat16* __restrict_
     const long long hw = (long long)H * W, qofs = (long long)qy * W + qx;
     float p[KK];
     pixel_softmax_f32<KK>(logits + (long long)b * KK * hw + qofs, hw, p);   // every lane: same loads (broadcast)
-    AxisTap<float> tx[K], ty[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-        tx[j] = axis_tap<float>(qfx, j - K / 2, qx, Ws);
-        ty[j] = axis_tap<float>(qfy, j - K / 2, qy, Hs);
-    }
     const long long spl = (long long)Hs * Ws;
     const long long sc = NHWC ? 1 : spl, sp = NHWC ? C : 1;     // element strides: channel, position
     const __nv_bfloat16* sb = NHWC ? src + (long long)b * spl * C + c0 : src + ((long long)b * C + c0) * spl;
@@ -245,17 +240,20 @@ __device__ __forceinline__ void irregular_pixel(const __nv_bfloat16* __restrict_
     for (int c = lane; c < CN; c += 32) {
         const __nv_bfloat16* s = sb + c * sc;
         float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < K; ++i)
-#pragma unroll
+#pragma unroll 1
+        for (int i = 0; i < K; ++i) {      // rolled on purpose (rare path): keeps the tap table out of the registers
+            const AxisTap<float> ty = axis_tap<float>(qfy, i - K / 2, qy, Hs);
+#pragma unroll 1
             for (int j = 0; j < K; ++j) {
+                const AxisTap<float> tx = axis_tap<float>(qfx, j - K / 2, qx, Ws);
                 float v = 0.f;
-                v += tx[j].wlo * ty[i].wlo * __bfloat162float(s[(ty[i].lo * Ws + tx[j].lo) * sp]);
-                v += tx[j].whi * ty[i].wlo * __bfloat162float(s[(ty[i].lo * Ws + tx[j].hi) * sp]);
-                v += tx[j].wlo * ty[i].whi * __bfloat162float(s[(ty[i].hi * Ws + tx[j].lo) * sp]);
-                v += tx[j].whi * ty[i].whi * __bfloat162float(s[(ty[i].hi * Ws + tx[j].hi) * sp]);
+                v += tx.wlo * ty.wlo * __bfloat162float(s[(ty.lo * Ws + tx.lo) * sp]);
+                v += tx.whi * ty.wlo * __bfloat162float(s[(ty.lo * Ws + tx.hi) * sp]);
+                v += tx.wlo * ty.whi * __bfloat162float(s[(ty.hi * Ws + tx.lo) * sp]);
+                v += tx.whi * ty.whi * __bfloat162float(s[(ty.hi * Ws + tx.hi) * sp]);
                 acc += p[i * K + j] * v;
             }
+        }
         acc *= 1.0f / static_cast<float>(KK);
         if (prev != nullptr) {
             const float qm = __bfloat162float(mask[(long long)b * hw + qofs]);

@@ -81,15 +81,13 @@ int gfla_debug_set_buffer(void* host_mapped_u64x8);
  * its timed region as `gpu_launches`. */
 unsigned long long gfla_debug_launch_count(void);
 
-/* Debug aid for tuning the forward tile kernels: cycles their warps spent blocked on the pipeline barriers.
+/* Debug aid for tuning the tile kernels: cycles their warps spent blocked on the pipeline barriers.
  * Only in profile builds of the library (GFLA_BUILD_PROFILE=1 at build time, -DGFLA_TC_PROFILE); a normal build
- * carries no timing code and returns GFLA_E_NOTSUP.  `which`: 0 = per-tile kernel, 1 = strip kernel.  Copies the
- * 32 counters collected since the last call into `out_u64x32` (HOST memory, may be NULL), clears them and switches
- * collection on (enable = 1) or off (0).  Index = role * 8 + kind; role 0 producer, 1 MMA issuer, 2 builders
- * (4 warps), 3 epilogue (4 warps); kind 0 source rows landed, 1 weight slabs built, 2 stage free, 3 accumulator
- * full, 4/6 accumulator drained, 5 tile info published, 6/7 explicit region timers; [7] = kernel cycles summed over
- * the CTAs.  Synchronises the device. */
-int gfla_debug_wait_profile(int which, int enable, unsigned long long* out_u64x32);
+ * carries no timing code and returns GFLA_E_NOTSUP.  `which`: 0 = per-tile forward kernel, 1 = strip forward kernel,
+ * 2 = fused backward kernel.  Copies the 64 counters collected since the last call into `out_u64x64` (HOST memory, may
+ * be NULL), clears them and switches collection on (enable = 1) or off (0).  Index = role * 8 + kind (roles and kinds per
+ * kernel: tools/wait_profile.py); [7] = kernel cycles summed over the CTAs.  Synchronises the device. */
+int gfla_debug_wait_profile(int which, int enable, unsigned long long* out_u64x64);
 
 /* Re-layout of a [B,C,H,W] feature tensor between planar NCHW and channels-last NHWC storage
  * (out of place; to_nhwc = 1: NCHW -> NHWC, 0: NHWC -> NCHW).  Not part of the reference's API: the
