@@ -20,7 +20,7 @@
 // Warp roles (4 warpgroups, persistent CTA, static round-robin over pixel groups; setmaxnreg moves registers from the
 // control warpgroup to the pixel team and the builders):
 //   warp 0        producer: tap bounding box from the flow, TMA of the grad_out tile and of the source-row stages;
-//   warp 1        MMA issuer: per block 2 Q stages, then the gs block (2 halves);   (warps 2, 3 idle)
+//   warp 1        MMA issuer of the Q stages, warp 2 MMA issuer of the gs blocks (2 channel halves each);   (warp 3 idle)
 //   warps 4-7     pixel team (thread = pixel): softmax, taps; per Q stage TMEM -> thread-private shared-memory row ->
 //                 picks its window entries with DYNAMIC SHARED addresses (no dynamically indexed registers, hence no
 //                 local-memory stack); after the last stage softmax-backward and the d/dflow formula;
@@ -123,7 +123,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
 
     if (threadIdx.x == 0) {
         mbar_init(g_full, 1);
-        mbar_init(g_empty, 1);
+        mbar_init(g_empty, 2);      // one commit from each MMA-issuing warp
         for (int i = 0; i < NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
         for (int i = 0; i < FB_NQ; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 4); }
         for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
@@ -184,73 +184,82 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 }
         }
       } else if (warp == 1) {
-        // ================================================================= MMA issuer
+        // ================================================================= MMA issuer 1: Q stages
+        // Two issuing warps, one per contraction: each blocks only on its own chain's barriers, so a grad_source block
+        // waiting for its epilogue (the TMA reduce-adds are the slow end of that chain) never holds back the Q stages.
         constexpr uint32_t idesc_q = make_idesc_f16(128, FB_QROWS * FB_BW, true, false, false);   // both K-major
-        constexpr uint32_t idesc_gs = make_idesc_f16(128, HN, true, true, true);                  // both MN-major
-        uint32_t it = 0, blk = 0, u = 0;
+        uint32_t it = 0;
         int gi = 0;
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
             mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x010500, gi);
             const GroupInfo inf = infos[gi % FB_NINFO];
-            const int nb4 = (inf.nrc + 1) / 2;
+            const int nst = inf.ncb * inf.nrc;
             mbar_wait(g_full, gi & 1, 0x010700, gi);
             const uint32_t g0 = smem_u32(smem + SM::OFF_G);
-            for (int cb = 0; cb < inf.ncb; ++cb)
-                for (int rb = 0; rb < nb4; ++rb, ++blk) {
-                    const int nq = min(2, inf.nrc - 2 * rb);
-                    // ---- Q stages of this block's rows
-                    for (int h = 0; h < nq; ++h, ++it) {
-                        const int slot = it % NS, buf = it % FB_NQ;
-                        mbar_wait(&s_full[slot], (it / NS) & 1, 0x010000 | slot, it);
-                        mbar_wait(&q_empty[buf], ((it / FB_NQ) & 1) ^ 1, 0x010400 | buf, it);
-                        tc_fence_after();
-                        if (lane == 0) {
-                            const uint32_t b0 = smem_u32(smem + SM::OFF_S + slot * SM::S_STAGE);
-                            const uint32_t d_tmem = tmem_base + buf * 64;
+            for (int s = 0; s < nst; ++s, ++it) {
+                const int slot = it % NS, buf = it % FB_NQ;
+                mbar_wait(&s_full[slot], (it / NS) & 1, 0x010000 | slot, it);
+                mbar_wait(&q_empty[buf], ((it / FB_NQ) & 1) ^ 1, 0x010400 | buf, it);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t b0 = smem_u32(smem + SM::OFF_S + slot * SM::S_STAGE);
+                    const uint32_t d_tmem = tmem_base + buf * 64;
 #pragma unroll
-                            for (int cg = 0; cg < CN / 64; ++cg)
+                    for (int cg = 0; cg < CN / 64; ++cg)
 #pragma unroll
-                                for (int kk = 0; kk < 4; ++kk) {   // 16 channels = 32 bytes inside the 128-byte swizzled row
-                                    const uint64_t ad = make_smem_desc(g0 + cg * SM::G_CG + kk * 32, 16, 1024, kSwizzle128);
-                                    const uint64_t bd = make_smem_desc(b0 + cg * SM::S_CG + kk * 32, 16, 1024, kSwizzle128);
-                                    umma_f16(d_tmem, ad, bd, idesc_q, (cg | kk) != 0 ? 1u : 0u);
-                                }
-                            tc_commit(&s_empty[slot]);
-                            tc_commit(&q_full[buf]);
+                        for (int kk = 0; kk < 4; ++kk) {   // 16 channels = 32 bytes inside the 128-byte swizzled row
+                            const uint64_t ad = make_smem_desc(g0 + cg * SM::G_CG + kk * 32, 16, 1024, kSwizzle128);
+                            const uint64_t bd = make_smem_desc(b0 + cg * SM::S_CG + kk * 32, 16, 1024, kSwizzle128);
+                            umma_f16(d_tmem, ad, bd, idesc_q, (cg | kk) != 0 ? 1u : 0u);
                         }
-                        __syncwarp();
-                    }
-                    // ---- grad_source block: Wfull^T * G, one accumulator per channel half
-                    const int st = blk % NA;
-                    mbar_wait(&a_full[st], (blk / NA) & 1, 0x010100 | st, blk);
-                    const bool last = (cb == inf.ncb - 1) && (rb == nb4 - 1);
-#pragma unroll
-                    for (int hf = 0; hf < NH; ++hf, ++u) {
-                        const int buf = u & 1;
-                        mbar_wait(&gs_empty[buf], ((u >> 1) & 1) ^ 1, 0x010600 | buf, u);
-                        tc_fence_after();
-                        if (lane == 0) {
-                            const uint32_t a0 = smem_u32(smem + SM::OFF_A + st * SM::A_STAGE);
-                            const uint32_t d_tmem = tmem_base + SM::GS_COL0 + buf * HN;
-#pragma unroll
-                            for (int ks = 0; ks < 8; ++ks) {   // 16 pixels per MMA
-                                // A^T: M = positions (32 per slab, LBO = next slab), K = pixels (8 per 512-byte atom)
-                                const uint64_t ad = make_smem_desc(a0 + ks * 1024, FB_SLAB, 512, kSwizzle64);
-                                // B: N = channels of this half (64 per 128-byte row, LBO = next channel group), K = pixels
-                                const uint64_t bd = make_smem_desc(g0 + hf * (HN / 64) * SM::G_CG + ks * 2048, SM::G_CG, 1024, kSwizzle128);
-                                umma_f16(d_tmem, ad, bd, idesc_gs, ks != 0 ? 1u : 0u);
-                            }
-                            tc_commit(&gs_full[buf]);
-                            if (hf == NH - 1) {
-                                tc_commit(&a_empty[st]);
-                                if (last) tc_commit(g_empty);
-                            }
-                        }
-                        __syncwarp();
-                    }
+                    tc_commit(&s_empty[slot]);
+                    tc_commit(&q_full[buf]);
+                    if (s == nst - 1) tc_commit(g_empty);          // this warp's share of "the grad_out tile is no longer read"
                 }
+                __syncwarp();
+            }
         }
-      }   // warps 2, 3: no role (they pad the control warpgroup so that setmaxnreg can hand their registers on)
+      } else if (warp == 2) {
+        // ================================================================= MMA issuer 2: grad_source blocks (Wfull^T * G, one accumulator per channel half)
+        constexpr uint32_t idesc_gs = make_idesc_f16(128, HN, true, true, true);                  // both MN-major
+        uint32_t blk = 0, u = 0;
+        int gi = 0;
+        for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
+            mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x050500, gi);
+            const GroupInfo inf = infos[gi % FB_NINFO];
+            const int nblk = inf.ncb * ((inf.nrc + 1) / 2);
+            mbar_wait(g_full, gi & 1, 0x050700, gi);
+            const uint32_t g0 = smem_u32(smem + SM::OFF_G);
+            for (int bi = 0; bi < nblk; ++bi, ++blk) {
+                const int st = blk % NA;
+                mbar_wait(&a_full[st], (blk / NA) & 1, 0x050100 | st, blk);
+#pragma unroll
+                for (int hf = 0; hf < NH; ++hf, ++u) {
+                    const int buf = u & 1;
+                    mbar_wait(&gs_empty[buf], ((u >> 1) & 1) ^ 1, 0x050600 | buf, u);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a0 = smem_u32(smem + SM::OFF_A + st * SM::A_STAGE);
+                        const uint32_t d_tmem = tmem_base + SM::GS_COL0 + buf * HN;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {   // 16 pixels per MMA
+                            // A^T: M = positions (32 per slab, LBO = next slab), K = pixels (8 per 512-byte atom)
+                            const uint64_t ad = make_smem_desc(a0 + ks * 1024, FB_SLAB, 512, kSwizzle64);
+                            // B: N = channels of this half (64 per 128-byte row, LBO = next channel group), K = pixels
+                            const uint64_t bd = make_smem_desc(g0 + hf * (HN / 64) * SM::G_CG + ks * 2048, SM::G_CG, 1024, kSwizzle128);
+                            umma_f16(d_tmem, ad, bd, idesc_gs, ks != 0 ? 1u : 0u);
+                        }
+                        tc_commit(&gs_full[buf]);
+                        if (hf == NH - 1) {
+                            tc_commit(&a_empty[st]);
+                            if (bi == nblk - 1) tc_commit(g_empty);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+      }   // warp 3: no role (it pads the control warpgroup so that setmaxnreg can hand its registers on)
     } else if (warp < 8) {
         // ================================================================= pixel team: Q -> grad_flow, grad_logits
         reg_inc<FB_REG_PIX>();

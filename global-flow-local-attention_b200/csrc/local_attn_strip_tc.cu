@@ -54,7 +54,7 @@ struct StripSmem {
     static constexpr int OFF_O = OFF_W + 2 * W_TILE;           // 64B-swizzled: 512-byte aligned
     static constexpr int OFF_INFO = OFF_O + 4 * O_WARP;
     static constexpr int OFF_BAR = OFF_INFO + ST_NINFO * 32;
-    static constexpr int NBAR = 4 * NSTAGE + 4 + ST_NINFO;
+    static constexpr int NBAR = 6 * NSTAGE + 4 + ST_NINFO;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int TOTAL = OFF_TMEM + 16;
     static constexpr int ALLOC = TOTAL + 1024;                 // slack to align the base to 1024 B
@@ -117,10 +117,11 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
     uint64_t* full_s = bars;                      // [NSTAGE] TMA bytes landed
     uint64_t* full_a = bars + NSTAGE;             // [2][NSTAGE] 128 arrivals of builder team T: sub-slab T of the stage is written
-    uint64_t* empty = bars + 3 * NSTAGE;          // [NSTAGE] MMAs of the stage retired
-    uint64_t* acc_full = bars + 4 * NSTAGE;       // [2]
-    uint64_t* acc_empty = bars + 4 * NSTAGE + 2;  // [2]
-    uint64_t* info_full = bars + 4 * NSTAGE + 4;  // [ST_NINFO]
+    uint64_t* empty = bars + 3 * NSTAGE;          // [NSTAGE] MMAs of the stage retired: the source rows may be overwritten
+    uint64_t* empty_a = bars + 4 * NSTAGE;        // [2][NSTAGE] MMAs that read sub-slab T of the stage retired (only steps that fed team T's tile)
+    uint64_t* acc_full = bars + 6 * NSTAGE;       // [2]
+    uint64_t* acc_empty = bars + 6 * NSTAGE + 2;  // [2]
+    uint64_t* info_full = bars + 6 * NSTAGE + 4;  // [ST_NINFO]
     StripTile* infos = reinterpret_cast<StripTile*>(smem + SM::OFF_INFO);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_TMEM);
 
@@ -138,6 +139,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
             mbar_init(&full_s[i], 1); mbar_init(&full_a[i], 128); mbar_init(&full_a[NSTAGE + i], 128); mbar_init(&empty[i], 1);
+            mbar_init(&empty_a[i], 1); mbar_init(&empty_a[NSTAGE + i], 1);
         }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         for (int i = 0; i < ST_NINFO; ++i) mbar_init(&info_full[i], 1);
@@ -286,6 +288,8 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
                                 }
                         }
                         tc_commit(&empty[slot]);
+                        tc_commit(&empty_a[buf * NSTAGE + slot]);
+                        if (shared) tc_commit(&empty_a[(buf ^ 1) * NSTAGE + slot]);
                     }
                     __syncwarp();
                     started = true;
@@ -307,6 +311,8 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
         const uint32_t a_base = smem_u32(smem + SM::OFF_A) + T * SM::A_TILE + m * (FBW * 2);        // this pixel's row in sub-slab T of stage 0
         const uint32_t swz = ((m >> 1) & 3) << 4;                               // 64B-swizzle XOR of this row's 16B chunks
         uint64_t* my_full = full_a + T * NSTAGE;
+        uint64_t* my_empty = empty_a + T * NSTAGE;
+        uint32_t fill_par = 0u;                 // per slot: parity of the number of fills this team has made into it
         uint32_t it = 0, dirty = 0xffffffffu;   // slab rows start with unknown contents: treat them as dirty
         int ti = 0;
         // Raw inputs of this thread's pixel of the team's NEXT tile: loaded a whole tile pass before the window is built
@@ -388,11 +394,13 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
                 const bool cols_hit = have && live && e0 > -K1 && e0 < FBW && !(knobs & 1024);
                 for (int j = t.j0; j <= t.j1; ++j) {
                     if (strip_skipped(t, j)) continue;
-                    // Every step waits for its stage to be free, also the steps this team does not fill: a team that merely counted
-                    // steps could run phases ahead of the MMA warp, and a parity wait two phases early passes on the wrong phase.
+                    // Only the steps that feed this team's tile are waited for, on the team's OWN "sub-slab free" barrier (its phases
+                    // advance with this team's fills alone): the stage's `empty` barrier flips once per step, so a team that sat out
+                    // a few steps -- or was busy building its window -- would meet it two phases late and misread the parity.
                     const int slot = it % NSTAGE;
-                    mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x020200 | slot, it);
-                    if (own || strip_shared(t, j)) {        // this step feeds the team's tile: as the pass owner, or as the next tile of a shared step
+                    if (own || strip_shared(t, j)) {        // as the pass owner, or as the next tile of a shared step
+                        mbar_wait(&my_empty[slot], ((fill_par >> slot) & 1u) ^ 1u, 0x020200 | slot, it);
+                        fill_par ^= 1u << slot;
                         const long long tf0 = tc_profile_clock();
                         const uint32_t a_stage = a_base + slot * SM::A_STAGE;
                         const int R0 = 2 * j;

@@ -36,9 +36,10 @@ assert lib.gfla_debug_wait_profile(a.which, 0, ctypes.cast(out, ctypes.c_void_p)
 v = list(out)
 total = v[7]
 if a.which == 2:
-    names = {0: ("producer", 1), 1: ("mma", 1), 2: ("pixel team(x4)", 4), 3: ("slab builders(x4)", 4), 4: ("gs epilogue(x4)", 4)}
+    names = {0: ("producer", 1), 1: ("mma Q", 1), 5: ("mma gs", 1), 2: ("pixel team(x4)", 4), 3: ("slab builders(x4)", 4), 4: ("gs epilogue(x4)", 4)}
     kinds = {0: {2: "stage free", 6: "G free (prev group retired)"},
-             1: {0: "source stage landed", 1: "slabs built", 4: "Q acc drained", 5: "info", 6: "gs acc drained", 7: "G landed"},
+             1: {0: "source stage landed", 4: "Q acc drained", 5: "info", 7: "G landed"},
+             5: {1: "slabs built", 5: "info", 6: "gs acc drained", 7: "G landed"},
              2: {3: "Q acc full", 5: "info", 6: "[busy] softmax/taps + next loads", 7: "[busy] finalize"},
              3: {2: "slab stage free", 5: "info", 6: "[busy] window build"},
              4: {3: "gs acc full", 5: "info"}}
