@@ -37,13 +37,24 @@ constexpr int FB_BW = 32;            // source positions per row segment
 constexpr int FB_QROWS = 2;          // source rows per Q stage (N = 64)
 constexpr int FB_GROWS = 4;          // source rows per gs block (M = 128)
 constexpr int FB_SLAB = 128 * FB_BW * 2;   // [128 pixels][32 positions] bf16, 64-byte rows, 64B swizzle
-constexpr int FB_NQ = 4;             // Q accumulator buffers
 constexpr int FB_NINFO = 8;
 constexpr int FB_THREADS = 512;       // 4 warpgroups: {producer, MMA, 2 idle}, pixel team, slab builders, gs epilogue
 constexpr int FB_QS_STRIDE = 144;    // bytes per thread row of the Q staging (32 fp32 + 16: 16-byte stores of 8 lanes tile all banks)
 
-template <int CN>
+// schedule of one pixel group (32-byte slots): tap bounding box origin, column blocks, 2-row chunks, and the width (24 / 28 / 32
+// positions) of the LAST column block's reduce-add box -- the TMA reduce-adds are the slow end of the grad_source chain
+// (L2 reduction throughput), so boxes are clipped to the footprint: the last column block to its width, the last row block to 2
+// rows when the footprint ends in its first half.
+struct FbInfo { int x0, y0, ncb, nrc, wlast, pad0, pad1, pad2; };
+struct FbReduceMaps { CUtensorMap m[6]; };   // [width 24, 28, 32][rows 2, 4]
+
+// QA_TMEM: the A operand of the Q stages (the grad_out tile, K-major) is copied ONCE per group from shared memory into TMEM
+// (tcgen05.cp) and every Q MMA reads it from there.  Shared-memory bandwidth (128 B/clk) is what this kernel runs out of: with
+// A in shared memory each 64-position stage re-reads the whole 64 KB tile; with A in TMEM only the source rows are read.
+template <int CN, bool QA_TMEM>
 struct SmemFB {
+    static constexpr int NQ = QA_TMEM ? 2 : 4;                 // Q accumulator buffers of 64 TMEM columns
+    static constexpr int GA_COL0 = NQ * 64;                    // TMEM: grad_out tile as A operand, CN/2 columns (QA_TMEM only)
     static constexpr int NS = CN == 256 ? 2 : 4;               // source-row stages
     static constexpr int NA = CN == 256 ? 1 : 2;               // weight-slab stages (one gs block each)
     static constexpr int NH = CN >= 128 ? 2 : 1;               // channel halves of a gs block
@@ -61,15 +72,15 @@ struct SmemFB {
     static constexpr int OFF_W = OFF_O + 2 * O_BUF;
     static constexpr int OFF_QS = OFF_W + 36 * 128 * 2;
     static constexpr int OFF_INFO = OFF_QS + 128 * FB_QS_STRIDE;
-    static constexpr int OFF_BAR = OFF_INFO + FB_NINFO * 16;
-    static constexpr int NBAR = 2 + 2 * NS + 2 * FB_NQ + 2 * NA + 4 + FB_NINFO;
+    static constexpr int OFF_BAR = OFF_INFO + FB_NINFO * 32;
+    static constexpr int NBAR = 2 + 2 * NS + 2 * NQ + 2 * NA + 4 + FB_NINFO;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int ALLOC = OFF_TMEM + 16 + 1024;
-    static constexpr int GS_COL0 = FB_NQ * 64;                 // TMEM column of the first grad_source accumulator
+    static constexpr int GS_COL0 = 256;                        // TMEM column of the first grad_source accumulator
 };
-static_assert(SmemFB<256>::ALLOC <= 232448, "shared memory budget");
-static_assert(SmemFB<256>::OFF_O % 1024 == 0 && SmemFB<128>::OFF_O % 1024 == 0 && SmemFB<64>::OFF_O % 1024 == 0, "staging alignment");
-static_assert(SmemFB<256>::OFF_A % 1024 == 0 && SmemFB<128>::OFF_A % 1024 == 0 && SmemFB<64>::OFF_A % 1024 == 0, "slab alignment");
+static_assert(SmemFB<256, false>::ALLOC <= 232448, "shared memory budget");
+static_assert(SmemFB<256, false>::OFF_O % 1024 == 0 && SmemFB<128, false>::OFF_O % 1024 == 0 && SmemFB<64, false>::OFF_O % 1024 == 0, "staging alignment");
+static_assert(SmemFB<256, false>::OFF_A % 1024 == 0 && SmemFB<128, false>::OFF_A % 1024 == 0 && SmemFB<64, false>::OFF_A % 1024 == 0, "slab alignment");
 
 __device__ __forceinline__ void fb_named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -89,15 +100,15 @@ __device__ __forceinline__ float lds_f32(uint32_t a) {
     return v;
 }
 
-template <int K, int CN>
+template <int K, int CN, bool QA_TMEM>
 __global__ void __launch_bounds__(FB_THREADS, 1)
 k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_s,
-                       const __grid_constant__ CUtensorMap tmap_gs, const __nv_bfloat16* __restrict__ src,
+                       const __grid_constant__ FbReduceMaps tmaps_gs, const __nv_bfloat16* __restrict__ src,
                        const float* __restrict__ flow, const __nv_bfloat16* __restrict__ logits,
                        const __nv_bfloat16* __restrict__ gout, __nv_bfloat16* __restrict__ gsrc, float* __restrict__ gflow,
                        __nv_bfloat16* __restrict__ glogits, int B, int C, int Hs, int Ws, int H, int W, int accumulate) {
-    using SM = SmemFB<CN>;
-    constexpr int K1 = K + 1, KK = K * K, NS = SM::NS, NA = SM::NA, NH = SM::NH, HN = SM::HN;
+    using SM = SmemFB<CN, QA_TMEM>;
+    constexpr int K1 = K + 1, KK = K * K, NS = SM::NS, NA = SM::NA, NH = SM::NH, HN = SM::HN, FB_NQ = SM::NQ;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
@@ -112,7 +123,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
     uint64_t* gs_full = a_empty + NA;                // [2] grad_source accumulator half complete
     uint64_t* gs_empty = gs_full + 2;                // [2] 4 epilogue warps drained it
     uint64_t* info_full = gs_empty + 2;              // [FB_NINFO]
-    GroupInfo* infos = reinterpret_cast<GroupInfo*>(smem + SM::OFF_INFO);
+    FbInfo* infos = reinterpret_cast<FbInfo*>(smem + SM::OFF_INFO);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_TMEM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -132,7 +143,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         fence_barrier_init();
         tma_prefetch_desc(&tmap_g);
         tma_prefetch_desc(&tmap_s);
-        tma_prefetch_desc(&tmap_gs);
+        for (int i = 0; i < 6; ++i) tma_prefetch_desc(&tmaps_gs.m[i]);
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
@@ -152,7 +163,8 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             group_bbox<K>(flow, b, gx0, gy0, H, W, Hs, Ws, lane, false, x0, y0, x1, y1);
             const int ncb = (x1 - x0 + FB_BW) / FB_BW, nrc = (y1 - y0 + FB_QROWS) / FB_QROWS;
             if (lane == 0) {
-                infos[gi % FB_NINFO] = GroupInfo{x0, y0, ncb, nrc};
+                const int wl = x1 - (x0 + FB_BW * (ncb - 1)) + 1;
+                infos[gi % FB_NINFO] = FbInfo{x0, y0, ncb, nrc, wl <= 24 ? 24 : (wl <= 28 ? 28 : 32), 0, 0, 0};
                 mbar_arrive(&info_full[gi % FB_NINFO]);
             }
             mbar_wait(g_empty, (gi & 1) ^ 1, 0x000600, gi);
@@ -192,10 +204,23 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         int gi = 0;
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
             mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x010500, gi);
-            const GroupInfo inf = infos[gi % FB_NINFO];
+            const FbInfo inf = infos[gi % FB_NINFO];
             const int nst = inf.ncb * inf.nrc;
             mbar_wait(g_full, gi & 1, 0x010700, gi);
             const uint32_t g0 = smem_u32(smem + SM::OFF_G);
+            if (QA_TMEM) {
+                tc_fence_after();
+                if (lane == 0) {
+#pragma unroll
+                    for (int cg = 0; cg < CN / 64; ++cg)
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)     // [128 px][16 channels] -> 8 TMEM columns
+                            tmem_cp_128x256b(tmem_base + SM::GA_COL0 + (cg * 4 + kk) * 8,
+                                             make_smem_desc(g0 + cg * SM::G_CG + kk * 32, 16, 1024, kSwizzle128));
+                    tc_commit(g_empty);        // the Q chain is done with the shared-memory copy of the tile
+                }
+                __syncwarp();
+            }
             for (int s = 0; s < nst; ++s, ++it) {
                 const int slot = it % NS, buf = it % FB_NQ;
                 mbar_wait(&s_full[slot], (it / NS) & 1, 0x010000 | slot, it);
@@ -208,13 +233,17 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                     for (int cg = 0; cg < CN / 64; ++cg)
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {   // 16 channels = 32 bytes inside the 128-byte swizzled row
-                            const uint64_t ad = make_smem_desc(g0 + cg * SM::G_CG + kk * 32, 16, 1024, kSwizzle128);
                             const uint64_t bd = make_smem_desc(b0 + cg * SM::S_CG + kk * 32, 16, 1024, kSwizzle128);
-                            umma_f16(d_tmem, ad, bd, idesc_q, (cg | kk) != 0 ? 1u : 0u);
+                            if (QA_TMEM) {
+                                umma_f16_ts(d_tmem, tmem_base + SM::GA_COL0 + (cg * 4 + kk) * 8, bd, idesc_q, (cg | kk) != 0 ? 1u : 0u);
+                            } else {
+                                const uint64_t ad = make_smem_desc(g0 + cg * SM::G_CG + kk * 32, 16, 1024, kSwizzle128);
+                                umma_f16(d_tmem, ad, bd, idesc_q, (cg | kk) != 0 ? 1u : 0u);
+                            }
                         }
                     tc_commit(&s_empty[slot]);
                     tc_commit(&q_full[buf]);
-                    if (s == nst - 1) tc_commit(g_empty);          // this warp's share of "the grad_out tile is no longer read"
+                    if (!QA_TMEM && s == nst - 1) tc_commit(g_empty);   // this warp's share of "the grad_out tile is no longer read"
                 }
                 __syncwarp();
             }
@@ -226,7 +255,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         int gi = 0;
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
             mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x050500, gi);
-            const GroupInfo inf = infos[gi % FB_NINFO];
+            const FbInfo inf = infos[gi % FB_NINFO];
             const int nblk = inf.ncb * ((inf.nrc + 1) / 2);
             mbar_wait(g_full, gi & 1, 0x050700, gi);
             const uint32_t g0 = smem_u32(smem + SM::OFF_G);
@@ -312,7 +341,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             for (int i = 0; i < K1 * K1; ++i) Qw[i] = 0.f;
 
             mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x020500, gi);
-            const GroupInfo inf = infos[gi % FB_NINFO];
+            const FbInfo inf = infos[gi % FB_NINFO];
             for (int cb = 0; cb < inf.ncb; ++cb) {
                 const int C0 = inf.x0 + cb * FB_BW;
                 for (int rc = 0; rc < inf.nrc; ++rc, ++it) {
@@ -484,7 +513,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             if (g + (int)gridDim.x < ngroups) load_pixel(g + gridDim.x);
             tc_profile_add(3, 6, tc_profile_clock() - tw0);          // window of this group, raw loads of the next
             mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x030500, gi);
-            const GroupInfo inf = infos[gi % FB_NINFO];
+            const FbInfo inf = infos[gi % FB_NINFO];
             const int nb4 = (inf.nrc + 1) / 2;
             for (int cb = 0; cb < inf.ncb; ++cb) {
                 const int e0 = X0 - (inf.x0 + cb * FB_BW);
@@ -561,10 +590,16 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 }
             }
             mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x000500 | 0x40000, gi);
-            const GroupInfo inf = infos[gi % FB_NINFO];
+            const FbInfo inf = infos[gi % FB_NINFO];
             const int nb4 = (inf.nrc + 1) / 2;
             for (int cb = 0; cb < inf.ncb; ++cb)
                 for (int rb = 0; rb < nb4; ++rb) {
+                    // reduce-add box of this block: [bw positions][brows rows]; staging rows are packed in the same order
+                    const int bw = (cb == inf.ncb - 1) ? inf.wlast : FB_BW;
+                    const int brows = (rb == nb4 - 1 && (inf.nrc & 1)) ? 2 : FB_GROWS;
+                    const CUtensorMap* rmap = &tmaps_gs.m[((bw - 24) >> 2) * 2 + (brows >> 2)];
+                    const int lin = (t >> 5) * bw + (t & 31);                 // this thread's row of the staging tile
+                    const bool in_box = (t & 31) < bw && (t >> 5) < brows;
 #pragma unroll 1
                     for (int hf = 0; hf < NH; ++hf, ++u) {
                         const int buf = u & 1;
@@ -582,8 +617,9 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                                 __syncwarp();
                                 if (lane == 0) mbar_arrive(&gs_empty[buf]);
                             }
-                            const uint32_t ob = o_base + (oi & 1) * SM::O_BUF + t * 128;
+                            const uint32_t ob = o_base + (oi & 1) * SM::O_BUF + lin * 128;
                             fb_named_bar_sync(1, 128);        // staging buffer (oi & 1) is free (issuer waited on its reader)
+                            if (in_box) {
 #pragma unroll
                             for (int ch = 0; ch < 8; ++ch) {  // 8 x 16 bytes = 64 channels, 128B swizzle (chunk ^= row & 7)
                                 const uint32_t* v = ch < 4 ? v0 + 8 * ch : v1 + 8 * (ch - 4);
@@ -593,12 +629,13 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                                     const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
                                     pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
                                 }
-                                sts128(ob + ((ch ^ (t & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+                                sts128(ob + ((ch ^ (lin & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+                            }
                             }
                             fence_proxy_async_smem();
                             fb_named_bar_sync(2, 128);        // tile complete
                             if (issuer) {
-                                tma_reduce_add_4d(&tmap_gs, o_base + (oi & 1) * SM::O_BUF, hf * HN + cg * 64, inf.x0 + cb * FB_BW,
+                                tma_reduce_add_4d(rmap, o_base + (oi & 1) * SM::O_BUF, hf * HN + cg * 64, inf.x0 + cb * FB_BW,
                                                   inf.y0 + rb * FB_GROWS, b);
                                 bulk_commit();
                                 bulk_wait_read<1>();          // the OTHER buffer's reduce has finished reading smem
@@ -615,12 +652,13 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
     tc_profile_total(t_start);
 }
 
-template <int K, int CN>
+template <int K, int CN, bool QA_TMEM>
 static int launch_fused(const void* src, const void* flow, const void* logits, const void* gout, void* gsrc, void* gflow,
                         void* glogits, int B, int C, int Hs, int Ws, int H, int W, int accumulate, cudaStream_t st_) {
     static const PFN_tmapEncodeTiled enc = tmap_encoder();
     if (enc == nullptr) return GFLA_E_NOTSUP;
-    CUtensorMap tg, ts, tgs;
+    CUtensorMap tg, ts;
+    FbReduceMaps tgs;
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const cuuint64_t odim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t ostr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
@@ -628,24 +666,29 @@ static int launch_fused(const void* src, const void* flow, const void* logits, c
     const cuuint64_t sstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)Ws * C * 2, (cuuint64_t)Hs * Ws * C * 2};
     const cuuint32_t gbox[4] = {64, GW, GH, 1};                 // grad_out tile: 16 x 8 pixels
     const cuuint32_t sbox[4] = {64, FB_BW, FB_QROWS, 1};        // source rows of one Q stage
-    const cuuint32_t rbox[4] = {64, FB_BW, FB_GROWS, 1};        // reduce-add tile: 32 x 4 source positions
+
     // all three maps exist before anything is written (a failure here leaves the caller's buffers untouched)
     if (enc(&tg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(gout), odim, ostr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
         enc(&ts, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), sdim, sstr, sbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
-        enc(&tgs, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, gsrc, sdim, sstr, rbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return GFLA_E_NOTSUP;
-    auto kern = k_local_attn_bwd_fused<K, CN>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemFB<CN>::ALLOC);
+    for (int wi = 0; wi < 3; ++wi)
+        for (int ri = 0; ri < 2; ++ri) {     // reduce-add tiles: (24 | 28 | 32) x (2 | 4) source positions
+            const cuuint32_t rbox[4] = {64, (cuuint32_t)(24 + 4 * wi), (cuuint32_t)(ri == 0 ? 2 : FB_GROWS), 1};
+            if (enc(&tgs.m[wi * 2 + ri], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, gsrc, sdim, sstr, rbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return GFLA_E_NOTSUP;
+        }
+    auto kern = k_local_attn_bwd_fused<K, CN, QA_TMEM>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemFB<CN, QA_TMEM>::ALLOC);
     if (e != cudaSuccess) return static_cast<int>(e);
     if (!accumulate) {   // the reduce-adds need a zero-filled grad_source; nothing was written before this point
         const int z = zero_async(gsrc, (size_t)B * C * Hs * Ws * 2, st_);
         if (z != GFLA_OK) return z;
     }
     const int ngroups = B * ((H + GH - 1) / GH) * ((W + GW - 1) / GW);
-    kern<<<(unsigned)min(ngroups, sm_count()), FB_THREADS, SmemFB<CN>::ALLOC, st_>>>(
+    kern<<<(unsigned)min(ngroups, sm_count()), FB_THREADS, SmemFB<CN, QA_TMEM>::ALLOC, st_>>>(
         tg, ts, tgs, (const __nv_bfloat16*)src, (const float*)flow, (const __nv_bfloat16*)logits, (const __nv_bfloat16*)gout,
         (__nv_bfloat16*)gsrc, (float*)gflow, (__nv_bfloat16*)glogits, B, C, Hs, Ws, H, W, accumulate);
     return launch_status();
@@ -663,8 +706,11 @@ bool local_attn_bwd_fused_supported(int C, int k, const void* src) {
 // other than the launch itself) and all three gradients are overwritten; 1: everything is added into the caller's buffers.
 int local_attn_bwd_fused_tc(const void* src, const void* flow, const void* logits, const void* gout, void* gsrc, void* gflow,
                             void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate, cudaStream_t st_) {
+    const bool qa_tmem = tc::tune_knob("GFLA_BWD_QA_TMEM", 0) != 0;      // experiment: A operand of the Q stages from TMEM
 #define GFLA_FB_CASE(K_, CN_) \
-    if (k == K_ && C == CN_) return tc::launch_fused<K_, CN_>(src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, accumulate, st_);
+    if (k == K_ && C == CN_) \
+        return qa_tmem ? tc::launch_fused<K_, CN_, true>(src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, accumulate, st_) \
+                       : tc::launch_fused<K_, CN_, false>(src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, accumulate, st_);
     GFLA_FB_CASE(5, 256) GFLA_FB_CASE(5, 128) GFLA_FB_CASE(5, 64)
     GFLA_FB_CASE(3, 256) GFLA_FB_CASE(3, 128) GFLA_FB_CASE(3, 64)
 #undef GFLA_FB_CASE

@@ -47,6 +47,8 @@ else:
     names = {0: ("producer", 1), 1: ("mma", 1), 2: ("builders(x8)" if a.which == 1 else "builders(x4)", 8 if a.which == 1 else 4), 3: ("epilogue(x4)", 4)}
     k = {0: "full_s", 1: "full_a", 2: "empty", 3: "acc_full", 4: "acc_empty", 5: "info", 6: "region6", 7: "region7"}
     kinds = {r: dict(k) for r in range(4)}
+if total == 0:
+    print("raw counters:", v)
 print(f"kernel cycles per CTA per launch: {total / iters / 148:.0f}")
 for r, (nm, nw) in names.items():
     parts = []
