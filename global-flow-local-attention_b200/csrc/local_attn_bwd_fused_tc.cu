@@ -155,45 +155,69 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
       reg_dec<FB_REG_CTRL>();
       if (warp == 0) {
         // ================================================================= producer
+        // Per group: publish the schedule, queue the first source-row stages (their slots free up while the previous
+        // group's tail is still in the tensor pipe), then -- once every MMA of the previous group has retired -- the
+        // grad_out tile, then the remaining stages.  The flow of the NEXT group is loaded before the stage loop and reduced
+        // to its bounding box after it, so that latency never sits between two groups; its grad_out tile and source rows
+        // are then pulled into L2 (with only NS stages in flight, a stage that had to come from HBM would expose the whole
+        // DRAM latency once per stage).
         uint32_t it = 0;
         int gi = 0;
+        int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+        if (blockIdx.x < ngroups) {
+            const int g = blockIdx.x;
+            group_bbox<K>(flow, g / (gxn * gyn), (g % gxn) * GW, ((g / gxn) % gyn) * GH, H, W, Hs, Ws, lane, false, x0, y0, x1, y1);
+        }
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
             const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
-            int x0, y0, x1, y1;
-            group_bbox<K>(flow, b, gx0, gy0, H, W, Hs, Ws, lane, false, x0, y0, x1, y1);
-            const int ncb = (x1 - x0 + FB_BW) / FB_BW, nrc = (y1 - y0 + FB_QROWS) / FB_QROWS;
+            const int ncb = (x1 - x0 + FB_BW) / FB_BW, nrc = (y1 - y0 + FB_QROWS) / FB_QROWS, nst = ncb * nrc;
             if (lane == 0) {
                 const int wl = x1 - (x0 + FB_BW * (ncb - 1)) + 1;
                 infos[gi % FB_NINFO] = FbInfo{x0, y0, ncb, nrc, wl <= 24 ? 24 : (wl <= 28 ? 28 : 32), 0, 0, 0};
                 mbar_arrive(&info_full[gi % FB_NINFO]);
             }
+            const int gn = g + gridDim.x;
+            const bool has_next = gn < ngroups;
+            const int ngx0 = (gn % gxn) * GW, ngy0 = ((gn / gxn) % gyn) * GH, nb = gn / (gxn * gyn);
+            TileFlow nf;
+            if (has_next) tile_flow_load(flow, nb, ngx0, ngy0, H, W, lane, nf);
+            const int cx0 = x0, cy0 = y0;
+            auto load_stage = [&](int s) {
+                const int cb = s / nrc, rc = s - cb * nrc, slot = it % NS;
+                mbar_wait(&s_empty[slot], ((it / NS) & 1) ^ 1, 0x000200 | slot, it);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&s_full[slot], SM::S_STAGE);
+#pragma unroll
+                    for (int cg = 0; cg < CN / 64; ++cg)
+                        tma_load_4d(smem + SM::OFF_S + slot * SM::S_STAGE + cg * SM::S_CG, &tmap_s, &s_full[slot], cg * 64,
+                                    cx0 + cb * FB_BW, cy0 + rc * FB_QROWS, b);
+                }
+                __syncwarp();
+                ++it;
+            };
+            int s = 0;
+            for (; s < nst && s < NS; ++s) load_stage(s);
             mbar_wait(g_empty, (gi & 1) ^ 1, 0x000600, gi);
-            if (lane == 0) {
+            if (elect_one()) {
                 mbar_arrive_expect_tx(g_full, SM::G_BYTES);
 #pragma unroll
                 for (int cg = 0; cg < CN / 64; ++cg)
                     tma_load_4d(smem + SM::OFF_G + cg * SM::G_CG, &tmap_g, g_full, cg * 64, gx0, gy0, b);
-                const int gn = g + gridDim.x;          // pull the next group's grad_out tile into L2 meanwhile
-                if (gn < ngroups) {
+                if (has_next) {
 #pragma unroll
-                    for (int cg = 0; cg < CN / 64; ++cg)
-                        tma_prefetch_4d(&tmap_g, cg * 64, (gn % gxn) * GW, ((gn / gxn) % gyn) * GH, gn / (gxn * gyn));
+                    for (int cg = 0; cg < CN / 64; ++cg) tma_prefetch_4d(&tmap_g, cg * 64, ngx0, ngy0, nb);
                 }
             }
             __syncwarp();
-            for (int cb = 0; cb < ncb; ++cb)
-                for (int rc = 0; rc < nrc; ++rc, ++it) {
-                    const int slot = it % NS;
-                    mbar_wait(&s_empty[slot], ((it / NS) & 1) ^ 1, 0x000200 | slot, it);
-                    if (lane == 0) {
-                        mbar_arrive_expect_tx(&s_full[slot], SM::S_STAGE);
-#pragma unroll
-                        for (int cg = 0; cg < CN / 64; ++cg)
-                            tma_load_4d(smem + SM::OFF_S + slot * SM::S_STAGE + cg * SM::S_CG, &tmap_s, &s_full[slot], cg * 64,
-                                        x0 + cb * FB_BW, y0 + rc * FB_QROWS, b);
-                    }
-                    __syncwarp();
+            for (; s < nst; ++s) load_stage(s);
+            if (has_next) {
+                tile_bbox_reduce<K>(nf, ngx0, ngy0, H, W, Hs, Ws, lane, false, x0, y0, x1, y1);
+                const int pcb = (x1 - x0 + FB_BW) / FB_BW, prc = (y1 - y0 + FB_QROWS) / FB_QROWS;
+                for (int i = lane; i < pcb * prc * (CN / 64); i += 32) {
+                    const int cg = i % (CN / 64), st = i / (CN / 64), cb = st / prc, rc = st - cb * prc;
+                    tma_prefetch_4d(&tmap_s, cg * 64, x0 + cb * FB_BW, y0 + rc * FB_QROWS, nb);
                 }
+            }
         }
       } else if (warp == 1) {
         // ================================================================= MMA issuer 1: Q stages
@@ -210,7 +234,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             const uint32_t g0 = smem_u32(smem + SM::OFF_G);
             if (QA_TMEM) {
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
 #pragma unroll
                     for (int cg = 0; cg < CN / 64; ++cg)
 #pragma unroll
@@ -226,7 +250,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 mbar_wait(&s_full[slot], (it / NS) & 1, 0x010000 | slot, it);
                 mbar_wait(&q_empty[buf], ((it / FB_NQ) & 1) ^ 1, 0x010400 | buf, it);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t b0 = smem_u32(smem + SM::OFF_S + slot * SM::S_STAGE);
                     const uint32_t d_tmem = tmem_base + buf * 64;
 #pragma unroll
@@ -267,7 +291,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                     const int buf = u & 1;
                     mbar_wait(&gs_empty[buf], ((u >> 1) & 1) ^ 1, 0x050600 | buf, u);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (elect_one()) {
                         const uint32_t a0 = smem_u32(smem + SM::OFF_A + st * SM::A_STAGE);
                         const uint32_t d_tmem = tmem_base + SM::GS_COL0 + buf * HN;
 #pragma unroll
@@ -537,7 +561,6 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         // ================================================================= grad_source epilogue (thread = position of the block)
         const int q = warp & 3, t = q * 32 + lane;          // block row t/32, column t%32 (as a PIXEL index for the irregular pass: 16 wide)
         const uint32_t o_base = smem_u32(smem + SM::OFF_O);
-        const bool issuer = (warp == 12 && lane == 0);
         uint32_t u = 0, oi = 0;   // oi: running index of the staging tile (alternates between the two buffers)
         int gi = 0;
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
@@ -634,7 +657,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                             }
                             fence_proxy_async_smem();
                             fb_named_bar_sync(2, 128);        // tile complete
-                            if (issuer) {
+                            if (warp == 12 && elect_one()) {
                                 tma_reduce_add_4d(rmap, o_base + (oi & 1) * SM::O_BUF, hf * HN + cg * 64, inf.x0 + cb * FB_BW,
                                                   inf.y0 + rb * FB_GROWS, b);
                                 bulk_commit();
@@ -644,7 +667,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                     }
                 }
         }
-        if (issuer) bulk_wait<0>();
+        if (warp == 12 && elect_one()) bulk_wait<0>();
     }
     tc_fence_before();
     __syncthreads();

@@ -102,7 +102,7 @@ k_local_attn_bwd_q_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
                 mbar_arrive(&info_full[gi % Q_NINFO]);
             }
             mbar_wait(g_empty, (gi & 1) ^ 1, 0x000600, gi);
-            if (lane == 0) {
+            if (elect_one()) {
                 mbar_arrive_expect_tx(g_full, SM::G_BYTES);
 #pragma unroll
                 for (int cg = 0; cg < CN / 64; ++cg)
@@ -113,7 +113,7 @@ k_local_attn_bwd_q_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
                 for (int rc = 0; rc < nrc; ++rc, ++it) {
                     const int slot = it % Q_NS;
                     mbar_wait(&s_empty[slot], ((it / Q_NS) & 1) ^ 1, 0x000200 | slot, it);
-                    if (lane == 0) {
+                    if (elect_one()) {
                         mbar_arrive_expect_tx(&s_full[slot], SM::S_STAGE);
 #pragma unroll
                         for (int cg = 0; cg < CN / 64; ++cg)
@@ -138,7 +138,7 @@ k_local_attn_bwd_q_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_c
                 mbar_wait(&s_full[slot], (it / Q_NS) & 1, 0x010000 | slot, it);
                 mbar_wait(&acc_empty[buf], ((it / Q_NACC) & 1) ^ 1, 0x010400 | buf, it);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t a0 = smem_u32(smem + SM::OFF_G);
                     const uint32_t b0 = smem_u32(smem + SM::OFF_S + slot * SM::S_STAGE);
                     const uint32_t d_tmem = tmem_base + buf * 64;

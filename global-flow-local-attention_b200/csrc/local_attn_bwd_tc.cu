@@ -118,7 +118,7 @@ k_local_attn_bwd_gs_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 mbar_arrive(&info_full[gi % GS_NINFO]);
             }
             mbar_wait(g_empty, (gi & 1) ^ 1, 0x000600, gi);
-            if (lane == 0) {
+            if (elect_one()) {
                 mbar_arrive_expect_tx(g_full, SM::G_BYTES);
 #pragma unroll
                 for (int cg = 0; cg < CN / 64; ++cg)
@@ -141,7 +141,7 @@ k_local_attn_bwd_gs_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 mbar_wait(&a_full[st], (blk / GS_NA) & 1, 0x010100 | st, blk);
                 mbar_wait(&acc_empty[buf], ((blk >> 1) & 1) ^ 1, 0x010400 | buf, blk);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t a0 = smem_u32(smem + SM::OFF_A + st * SM::A_STAGE);
                     const uint32_t b0 = smem_u32(smem + SM::OFF_G);
                     const uint32_t d_tmem = tmem_base + buf * CN;

@@ -108,7 +108,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
                        int Ws, int H, int W, int ts, int knobs) {
     // `knobs` (environment GFLA_TC_KNOBS, default 0 = production) switch parts of the pipeline off for timing experiments
     // (results are wrong when set): bit 8 no output stores, bit 10 no weight scatter (slabs only zeroed), bit 11 no slab
-    // writes at all, bit 12 no MMAs, bit 13 no TMA loads.
+    // writes at all, bit 12 no MMAs, bit 13 no TMA loads, bit 14 no L2 prefetch of upcoming rows.
     using SM = StripSmem<CN>;
     constexpr int NSTAGE = SM::NSTAGE, FBW = ST_FBW, RCH = ST_RCH;
     constexpr int K1 = K + 1, KK = K * K;
@@ -201,7 +201,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
                     const int slot = it % NSTAGE;
                     mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x000200 | slot, it);
                     if (lane == 0 && (knobs & 8192)) mbar_arrive(&full_s[slot]);
-                    if (lane == 0 && !(knobs & 8192)) {
+                    if (!(knobs & 8192) && elect_one()) {
                         mbar_arrive_expect_tx(&full_s[slot], SM::S_STAGE);
 #pragma unroll
                         for (int rr = 0; rr < RCH; ++rr) {
@@ -221,6 +221,16 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
             if (pend) {
                 tile_bbox_reduce<K>(fr, pend_it.gx * GW, pend_it.ty * GH, H, W, Hs, Ws, lane, false, box1.x0, box1.y0, box1.x1, box1.y1);
                 unit1 = pend_it.unit;
+                // pull the source rows of the tile after next into L2 (two tile passes ahead of their TMA loads): with NSTAGE
+                // stages in flight a row chunk that must come from HBM exposes the DRAM latency once per stage
+                if (!(knobs & 16384)) {
+                    const int pj0 = box1.y0 >> 1, pj1 = box1.y1 >> 1, pcb = (box1.x1 - box1.x0 + FBW) / FBW;
+                    const int per = (pj1 - pj0 + 1) * RCH * (CN / 64);
+                    for (int i = lane; i < per * pcb; i += 32) {
+                        const int cb = i / per, r = i - cb * per, cg = r % (CN / 64), row = 2 * pj0 + r / (CN / 64);
+                        tma_prefetch_4d(&tmap_src, c0 + cg * 64, box1.x0 + cb * FBW, row, pend_it.b);
+                    }
+                }
             } else {
                 unit1 = -1;
             }
@@ -266,7 +276,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
                         par_a[buf ^ 1] ^= 1u << slot;
                     }
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (elect_one()) {
                         const uint32_t a0 = smem_u32(smem + SM::OFF_A + slot * SM::A_STAGE);
                         const uint32_t b0 = smem_u32(smem + SM::OFF_S + slot * SM::S_STAGE);
 #pragma unroll
@@ -296,7 +306,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
                     if (shared) next_started = true;
                     ++it;
                 }
-            if (lane == 0) tc_commit(&acc_full[buf]);
+            if (elect_one()) tc_commit(&acc_full[buf]);
             __syncwarp();
             started = next_started;   // false after the last tile of a strip (it never shares)
         }
@@ -474,7 +484,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
                             }
                         }
                     }
-                    if (lane == 0) bulk_wait_read<0>();   // the previous tile store has finished reading the staging buffer
+                    if (elect_one()) bulk_wait_read<0>();   // the previous tile store (same elected lane) has finished reading the staging buffer
                     __syncwarp();
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -488,7 +498,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0 && !(knobs & 256)) {
+                    if (!(knobs & 256) && elect_one()) {
                         tma_store_4d(&tmap_out, ob, c0 + cc * 32, gx * GW, ty * GH + 2 * q, b);
                         bulk_commit();
                     }
@@ -520,7 +530,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
                 // reference's literal 4-taps-per-(i,j) arithmetic, the warp shares one pixel (lanes split the channels)
                 unsigned todo = __ballot_sync(0xffffffffu, valid && !regular);
                 if (todo) {   // the tile stores above must have landed before these pixels are rewritten
-                    if (lane == 0) bulk_wait<0>();
+                    if (elect_one()) bulk_wait<0>();
                     __syncwarp();
                 }
                 while (todo) {
@@ -533,7 +543,7 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
             }
         }
     }
-    if (warp >= 12 && lane == 0) bulk_wait_read<0>();   // staging buffers stay valid until their last store has read them
+    if (warp >= 12 && elect_one()) bulk_wait_read<0>();   // staging buffers stay valid until their last store has read them
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 2 * CN >= 32 ? 2 * CN : 32);

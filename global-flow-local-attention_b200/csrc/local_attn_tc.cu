@@ -165,7 +165,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                 for (int rc = 0; rc < nrc; ++rc, ++it) {
                     const int slot = it % NSTAGE;
                     mbar_wait(&empty[slot], ((it / NSTAGE) & 1) ^ 1, 0x000200 | slot, it);
-                    if (lane == 0) {
+                    if (elect_one()) {
                         mbar_arrive_expect_tx(&full_s[slot], SM::S_STAGE);
 #pragma unroll
                         for (int rr = 0; rr < RCH; ++rr) {
@@ -201,7 +201,7 @@ k_local_attn_fwd_tc(const __grid_constant__ CUtensorMap tmap_src, const __nv_bfl
                 mbar_wait(&full_s[slot], par, 0x010000 | slot, it);
                 mbar_wait(&full_a[slot], par, 0x010100 | slot, it);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t a0 = smem_u32(smem + SM::OFF_A + slot * SM::A_STAGE);
                     const uint32_t b0 = smem_u32(smem + SM::OFF_S + slot * SM::S_STAGE);
 #pragma unroll

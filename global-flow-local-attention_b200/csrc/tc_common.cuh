@@ -160,6 +160,20 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, in
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+// One lane of a converged warp (the same one every time).  MMA issue must branch on THIS, not on `lane == 0`: after
+// elect.sync the compiler knows a single lane is live and moves descriptors to the uniform registers UTCHMMA wants with
+// one R2UR each; behind a plain lane test it emits a waterfall loop (ELECT / R2UR.BROADCAST / BRA.U.ANY) per operand,
+// ~100 cycles per MMA -- more than a 128x64x16 MMA takes to execute.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ------------------------------------------------------------------ TMEM / tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {  // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
