@@ -9,9 +9,10 @@
 // Per 16x8 pixel group the grad_out tile G[128 px][C] is brought into shared memory ONCE (TMA) and feeds two
 // tensor-core contractions that walk the group's tap footprint together:
 //
-//   Q stage   (2 source rows x 32 columns):  Dq[128 px][64 pos]  = G[128 px][C] * S[64 pos][C]^T
-//             both operands K-major TMA boxes; the per-pixel dot products Q[p,t] at the (k+1)^2 window positions
-//             are all that grad_flow / grad_logits need (local_attn_bwd_q_tc.cu);
+//   Q stage   (1 source row x 32 columns):   Dq[128 px][32 pos]  = G[128 px][C] * S[32 pos][C]^T
+//             G is copied once per group from shared memory into TENSOR memory (tcgen05.cp) and is the A operand of every
+//             stage from there; B = the source row, a K-major TMA box.  The per-pixel dot products Q[p,t] at the (k+1)^2
+//             window positions are all that grad_flow / grad_logits need (local_attn_bwd_q_tc.cu);
 //   gs block  (4 source rows x 32 columns):  Dgs[128 pos][C]     = Wfull^T[128 pos][128 px] * G[128 px][C]
 //             A = the forward kernel's weight slabs read MN-major, B = the same G tile read MN-major; the tile leaves
 //             as a TMA REDUCE-ADD box into grad_source (local_attn_bwd_tc.cu).  The accumulator is split into two
@@ -27,41 +28,40 @@
 //   warps 8-11    slab builders (thread = pixel): softmax, taps, collapsed window, weight slabs of every gs block;
 //   warps 12-15   gs epilogue (thread = source position): TMEM -> bf16 -> swizzled staging -> TMA reduce-add;
 //                 irregular pixels (non-consecutive taps) are scattered here with vector reductions.
-// TMEM: 4 x 64 columns of Q accumulators + 2 x C/2 (C = 64: 2 x 64) columns of grad_source accumulators.
+// TMEM: 4 x 32 columns of Q accumulators, C/2 columns holding G as an MMA operand, 2 x C/2 (C = 64: 2 x 64) columns of
+// grad_source accumulators.  Shared-memory bandwidth (128 B/clk: MMA operand fetch + TMA + staging) is the resource this kernel
+// runs out of first (ncu: l1tex__data_pipe_{tc,lsu}_wavefronts_mem_shared); keeping G in TMEM removes the largest single reader.
 #include "tile_window.cuh"
 
 namespace gfla {
 namespace tc {
 
 constexpr int FB_BW = 32;            // source positions per row segment
-constexpr int FB_QROWS = 2;          // source rows per Q stage (N = 64)
+constexpr int FB_QROWS = 1;          // source rows per Q stage (N = 32)
 constexpr int FB_GROWS = 4;          // source rows per gs block (M = 128)
 constexpr int FB_SLAB = 128 * FB_BW * 2;   // [128 pixels][32 positions] bf16, 64-byte rows, 64B swizzle
 constexpr int FB_NINFO = 8;
 constexpr int FB_THREADS = 512;       // 4 warpgroups: {producer, MMA, 2 idle}, pixel team, slab builders, gs epilogue
 constexpr int FB_QS_STRIDE = 144;    // bytes per thread row of the Q staging (32 fp32 + 16: 16-byte stores of 8 lanes tile all banks)
 
-// schedule of one pixel group (32-byte slots): tap bounding box origin, column blocks, 2-row chunks, and the width (24 / 28 / 32
+// schedule of one pixel group (32-byte slots): tap bounding box origin, column blocks, source rows, and the width (24 / 28 / 32
 // positions) of the LAST column block's reduce-add box -- the TMA reduce-adds are the slow end of the grad_source chain
 // (L2 reduction throughput), so boxes are clipped to the footprint: the last column block to its width, the last row block to 2
-// rows when the footprint ends in its first half.
-struct FbInfo { int x0, y0, ncb, nrc, wlast, pad0, pad1, pad2; };
+// rows when the footprint ends in its first half.  (A grad_source block covers 4 rows; Q stages walk the rows one by one.)
+struct FbInfo { int x0, y0, ncb, nrows, wlast, pad0, pad1, pad2; };
 struct FbReduceMaps { CUtensorMap m[6]; };   // [width 24, 28, 32][rows 2, 4]
 
-// QA_TMEM: the A operand of the Q stages (the grad_out tile, K-major) is copied ONCE per group from shared memory into TMEM
-// (tcgen05.cp) and every Q MMA reads it from there.  Shared-memory bandwidth (128 B/clk) is what this kernel runs out of: with
-// A in shared memory each 64-position stage re-reads the whole 64 KB tile; with A in TMEM only the source rows are read.
-template <int CN, bool QA_TMEM>
+template <int CN>
 struct SmemFB {
-    static constexpr int NQ = QA_TMEM ? 2 : 4;                 // Q accumulator buffers of 64 TMEM columns
-    static constexpr int GA_COL0 = NQ * 64;                    // TMEM: grad_out tile as A operand, CN/2 columns (QA_TMEM only)
-    static constexpr int NS = CN == 256 ? 2 : 4;               // source-row stages
+    static constexpr int NQ = 4;                               // Q accumulator buffers of 32 TMEM columns
+    static constexpr int GA_COL0 = 128;                        // TMEM: grad_out tile as the A operand of the Q stages, CN/2 columns
+    static constexpr int NS = 4;                               // source-row stages
     static constexpr int NA = CN == 256 ? 1 : 2;               // weight-slab stages (one gs block each)
     static constexpr int NH = CN >= 128 ? 2 : 1;               // channel halves of a gs block
     static constexpr int HN = CN / NH;                         // channels per half (multiple of 64)
     static constexpr int G_CG = 128 * 128;                     // [128 pixels][64 channels] bf16
     static constexpr int G_BYTES = (CN / 64) * G_CG;
-    static constexpr int S_CG = FB_QROWS * FB_BW * 128;        // [64 positions][64 channels] = 8 KB
+    static constexpr int S_CG = FB_QROWS * FB_BW * 128;        // [32 positions][64 channels] = 4 KB
     static constexpr int S_STAGE = (CN / 64) * S_CG;
     static constexpr int A_STAGE = FB_GROWS * FB_SLAB;         // 4 slabs
     static constexpr int O_BUF = 128 * 128;                    // staging: [128 positions][64 channels] bf16
@@ -78,9 +78,9 @@ struct SmemFB {
     static constexpr int ALLOC = OFF_TMEM + 16 + 1024;
     static constexpr int GS_COL0 = 256;                        // TMEM column of the first grad_source accumulator
 };
-static_assert(SmemFB<256, false>::ALLOC <= 232448, "shared memory budget");
-static_assert(SmemFB<256, false>::OFF_O % 1024 == 0 && SmemFB<128, false>::OFF_O % 1024 == 0 && SmemFB<64, false>::OFF_O % 1024 == 0, "staging alignment");
-static_assert(SmemFB<256, false>::OFF_A % 1024 == 0 && SmemFB<128, false>::OFF_A % 1024 == 0 && SmemFB<64, false>::OFF_A % 1024 == 0, "slab alignment");
+static_assert(SmemFB<256>::ALLOC <= 232448, "shared memory budget");
+static_assert(SmemFB<256>::OFF_O % 1024 == 0 && SmemFB<128>::OFF_O % 1024 == 0 && SmemFB<64>::OFF_O % 1024 == 0, "staging alignment");
+static_assert(SmemFB<256>::OFF_A % 1024 == 0 && SmemFB<128>::OFF_A % 1024 == 0 && SmemFB<64>::OFF_A % 1024 == 0, "slab alignment");
 
 __device__ __forceinline__ void fb_named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -100,14 +100,15 @@ __device__ __forceinline__ float lds_f32(uint32_t a) {
     return v;
 }
 
-template <int K, int CN, bool QA_TMEM>
+template <int K, int CN>
 __global__ void __launch_bounds__(FB_THREADS, 1)
 k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_s,
                        const __grid_constant__ FbReduceMaps tmaps_gs, const __nv_bfloat16* __restrict__ src,
                        const float* __restrict__ flow, const __nv_bfloat16* __restrict__ logits,
                        const __nv_bfloat16* __restrict__ gout, __nv_bfloat16* __restrict__ gsrc, float* __restrict__ gflow,
-                       __nv_bfloat16* __restrict__ glogits, int B, int C, int Hs, int Ws, int H, int W, int accumulate) {
-    using SM = SmemFB<CN, QA_TMEM>;
+                       __nv_bfloat16* __restrict__ glogits, int B, int C, int Hs, int Ws, int H, int W, int accumulate, int knobs) {
+    // `knobs` (environment GFLA_BWD_KNOBS, default 0): bit 0 = also pull the next group's source rows into L2 ahead of time
+    using SM = SmemFB<CN>;
     constexpr int K1 = K + 1, KK = K * K, NS = SM::NS, NA = SM::NA, NH = SM::NH, HN = SM::HN, FB_NQ = SM::NQ;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -170,10 +171,10 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         }
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
             const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
-            const int ncb = (x1 - x0 + FB_BW) / FB_BW, nrc = (y1 - y0 + FB_QROWS) / FB_QROWS, nst = ncb * nrc;
+            const int ncb = (x1 - x0 + FB_BW) / FB_BW, nrows = y1 - y0 + 1, nst = ncb * nrows;
             if (lane == 0) {
                 const int wl = x1 - (x0 + FB_BW * (ncb - 1)) + 1;
-                infos[gi % FB_NINFO] = FbInfo{x0, y0, ncb, nrc, wl <= 24 ? 24 : (wl <= 28 ? 28 : 32), 0, 0, 0};
+                infos[gi % FB_NINFO] = FbInfo{x0, y0, ncb, nrows, wl <= 24 ? 24 : (wl <= 28 ? 28 : 32), 0, 0, 0};
                 mbar_arrive(&info_full[gi % FB_NINFO]);
             }
             const int gn = g + gridDim.x;
@@ -183,7 +184,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             if (has_next) tile_flow_load(flow, nb, ngx0, ngy0, H, W, lane, nf);
             const int cx0 = x0, cy0 = y0;
             auto load_stage = [&](int s) {
-                const int cb = s / nrc, rc = s - cb * nrc, slot = it % NS;
+                const int cb = s / nrows, rc = s - cb * nrows, slot = it % NS;
                 mbar_wait(&s_empty[slot], ((it / NS) & 1) ^ 1, 0x000200 | slot, it);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&s_full[slot], SM::S_STAGE);
@@ -212,7 +213,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             for (; s < nst; ++s) load_stage(s);
             if (has_next) {
                 tile_bbox_reduce<K>(nf, ngx0, ngy0, H, W, Hs, Ws, lane, false, x0, y0, x1, y1);
-                const int pcb = (x1 - x0 + FB_BW) / FB_BW, prc = (y1 - y0 + FB_QROWS) / FB_QROWS;
+                const int pcb = (x1 - x0 + FB_BW) / FB_BW, prc = (knobs & 1) ? y1 - y0 + 1 : 0;
                 for (int i = lane; i < pcb * prc * (CN / 64); i += 32) {
                     const int cg = i % (CN / 64), st = i / (CN / 64), cb = st / prc, rc = st - cb * prc;
                     tma_prefetch_4d(&tmap_s, cg * 64, x0 + cb * FB_BW, y0 + rc * FB_QROWS, nb);
@@ -223,28 +224,27 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         // ================================================================= MMA issuer 1: Q stages
         // Two issuing warps, one per contraction: each blocks only on its own chain's barriers, so a grad_source block
         // waiting for its epilogue (the TMA reduce-adds are the slow end of that chain) never holds back the Q stages.
-        constexpr uint32_t idesc_q = make_idesc_f16(128, FB_QROWS * FB_BW, true, false, false);   // both K-major
+        constexpr uint32_t idesc_q = make_idesc_f16(128, FB_QROWS * FB_BW, true, false, false);   // A from TMEM, B K-major
         uint32_t it = 0;
         int gi = 0;
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
             mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x010500, gi);
             const FbInfo inf = infos[gi % FB_NINFO];
-            const int nst = inf.ncb * inf.nrc;
+            const int nst = inf.ncb * inf.nrows;
             mbar_wait(g_full, gi & 1, 0x010700, gi);
             const uint32_t g0 = smem_u32(smem + SM::OFF_G);
-            if (QA_TMEM) {
-                tc_fence_after();
-                if (elect_one()) {
+            tc_fence_after();
+            if (elect_one()) {
+                // G[128 px][CN] -> TMEM, 16 channels (8 columns) per copy; ordered before the MMAs below, after those of the last group
 #pragma unroll
-                    for (int cg = 0; cg < CN / 64; ++cg)
+                for (int cg = 0; cg < CN / 64; ++cg)
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)     // [128 px][16 channels] -> 8 TMEM columns
-                            tmem_cp_128x256b(tmem_base + SM::GA_COL0 + (cg * 4 + kk) * 8,
-                                             make_smem_desc(g0 + cg * SM::G_CG + kk * 32, 16, 1024, kSwizzle128));
-                    tc_commit(g_empty);        // the Q chain is done with the shared-memory copy of the tile
-                }
-                __syncwarp();
+                    for (int kk = 0; kk < 4; ++kk)
+                        tmem_cp_128x256b(tmem_base + SM::GA_COL0 + (cg * 4 + kk) * 8,
+                                         make_smem_desc(g0 + cg * SM::G_CG + kk * 32, 16, 1024, kSwizzle128));
+                tc_commit(g_empty);        // the Q chain is done with the shared-memory copy of the tile
             }
+            __syncwarp();
             for (int s = 0; s < nst; ++s, ++it) {
                 const int slot = it % NS, buf = it % FB_NQ;
                 mbar_wait(&s_full[slot], (it / NS) & 1, 0x010000 | slot, it);
@@ -252,22 +252,15 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t b0 = smem_u32(smem + SM::OFF_S + slot * SM::S_STAGE);
-                    const uint32_t d_tmem = tmem_base + buf * 64;
+                    const uint32_t d_tmem = tmem_base + buf * 32;
 #pragma unroll
                     for (int cg = 0; cg < CN / 64; ++cg)
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {   // 16 channels = 32 bytes inside the 128-byte swizzled row
-                            const uint64_t bd = make_smem_desc(b0 + cg * SM::S_CG + kk * 32, 16, 1024, kSwizzle128);
-                            if (QA_TMEM) {
-                                umma_f16_ts(d_tmem, tmem_base + SM::GA_COL0 + (cg * 4 + kk) * 8, bd, idesc_q, (cg | kk) != 0 ? 1u : 0u);
-                            } else {
-                                const uint64_t ad = make_smem_desc(g0 + cg * SM::G_CG + kk * 32, 16, 1024, kSwizzle128);
-                                umma_f16(d_tmem, ad, bd, idesc_q, (cg | kk) != 0 ? 1u : 0u);
-                            }
-                        }
+                        for (int kk = 0; kk < 4; ++kk)     // 16 channels = 32 bytes inside the 128-byte swizzled row
+                            umma_f16_ts(d_tmem, tmem_base + SM::GA_COL0 + (cg * 4 + kk) * 8,
+                                        make_smem_desc(b0 + cg * SM::S_CG + kk * 32, 16, 1024, kSwizzle128), idesc_q, (cg | kk) != 0 ? 1u : 0u);
                     tc_commit(&s_empty[slot]);
                     tc_commit(&q_full[buf]);
-                    if (!QA_TMEM && s == nst - 1) tc_commit(g_empty);   // this warp's share of "the grad_out tile is no longer read"
                 }
                 __syncwarp();
             }
@@ -280,7 +273,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
             mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x050500, gi);
             const FbInfo inf = infos[gi % FB_NINFO];
-            const int nblk = inf.ncb * ((inf.nrc + 1) / 2);
+            const int nblk = inf.ncb * ((inf.nrows + FB_GROWS - 1) / FB_GROWS);
             mbar_wait(g_full, gi & 1, 0x050700, gi);
             const uint32_t g0 = smem_u32(smem + SM::OFF_G);
             for (int bi = 0; bi < nblk; ++bi, ++blk) {
@@ -368,36 +361,28 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             const FbInfo inf = infos[gi % FB_NINFO];
             for (int cb = 0; cb < inf.ncb; ++cb) {
                 const int C0 = inf.x0 + cb * FB_BW;
-                for (int rc = 0; rc < inf.nrc; ++rc, ++it) {
-                    const int buf = it % FB_NQ, R0 = inf.y0 + rc * FB_QROWS;
-                    // which of the stage's two rows does any pixel of this warp need?  (warp-uniform: skipped rows are never read)
-                    bool need[FB_QROWS];
+                for (int rc = 0; rc < inf.nrows; ++rc, ++it) {
+                    const int buf = it % FB_NQ, R0 = inf.y0 + rc;
+                    // does any pixel of this warp need this row?  (warp-uniform: a row nobody needs is never read)
+                    bool need = false;
+                    if (live) {
 #pragma unroll
-                    for (int j = 0; j < FB_QROWS; ++j) {
-                        bool nd = false;
-                        if (live) {
-#pragma unroll
-                            for (int r = 0; r < K1; ++r) nd = nd || (clampi(Y0 + r, Hs - 1) == R0 + j);
-                            nd = nd && (clampi(X0 + K, Ws - 1) >= C0) && (clampi(X0, Ws - 1) < C0 + FB_BW);
-                        }
-                        need[j] = nd;
+                        for (int r = 0; r < K1; ++r) need = need || (clampi(Y0 + r, Hs - 1) == R0);
+                        need = need && (clampi(X0 + K, Ws - 1) >= C0) && (clampi(X0, Ws - 1) < C0 + FB_BW);
                     }
-                    const unsigned any0 = __ballot_sync(0xffffffffu, need[0]), any1 = __ballot_sync(0xffffffffu, need[1]);
+                    const unsigned any = __ballot_sync(0xffffffffu, need);
                     mbar_wait(&q_full[buf], (it / FB_NQ) & 1, 0x020300 | buf, it);
-                    tc_fence_after();
-                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 64;
-#pragma unroll
-                    for (int j = 0; j < FB_QROWS; ++j) {
-                        if ((j == 0 ? any0 : any1) == 0u) continue;
+                    if (any != 0u) {
+                        tc_fence_after();
                         uint32_t v[32];
-                        tmem_ld_32x32(taddr + j * 32, v);
+                        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 32, v);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 8; ++i) sts128(qs_row + i * 16, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                        if (need[j]) {
+                        if (need) {
 #pragma unroll
                             for (int r = 0; r < K1; ++r) {
-                                if (clampi(Y0 + r, Hs - 1) == R0 + j) {
+                                if (clampi(Y0 + r, Hs - 1) == R0) {
 #pragma unroll
                                     for (int c = 0; c < K1; ++c) {
                                         const int e = clampi(X0 + c, Ws - 1) - C0;
@@ -406,8 +391,8 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                                 }
                             }
                         }
+                        tc_fence_before();
                     }
-                    tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&q_empty[buf]);
                 }
@@ -538,7 +523,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             tc_profile_add(3, 6, tc_profile_clock() - tw0);          // window of this group, raw loads of the next
             mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x030500, gi);
             const FbInfo inf = infos[gi % FB_NINFO];
-            const int nb4 = (inf.nrc + 1) / 2;
+            const int nb4 = (inf.nrows + FB_GROWS - 1) / FB_GROWS;
             for (int cb = 0; cb < inf.ncb; ++cb) {
                 const int e0 = X0 - (inf.x0 + cb * FB_BW);
                 const bool cols_hit = live && e0 > -K1 && e0 < FB_BW;
@@ -614,12 +599,12 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             }
             mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x000500 | 0x40000, gi);
             const FbInfo inf = infos[gi % FB_NINFO];
-            const int nb4 = (inf.nrc + 1) / 2;
+            const int nb4 = (inf.nrows + FB_GROWS - 1) / FB_GROWS;
             for (int cb = 0; cb < inf.ncb; ++cb)
                 for (int rb = 0; rb < nb4; ++rb) {
                     // reduce-add box of this block: [bw positions][brows rows]; staging rows are packed in the same order
                     const int bw = (cb == inf.ncb - 1) ? inf.wlast : FB_BW;
-                    const int brows = (rb == nb4 - 1 && (inf.nrc & 1)) ? 2 : FB_GROWS;
+                    const int brows = (rb == nb4 - 1 && inf.nrows - FB_GROWS * rb <= 2) ? 2 : FB_GROWS;
                     const CUtensorMap* rmap = &tmaps_gs.m[((bw - 24) >> 2) * 2 + (brows >> 2)];
                     const int lin = (t >> 5) * bw + (t & 31);                 // this thread's row of the staging tile
                     const bool in_box = (t & 31) < bw && (t >> 5) < brows;
@@ -675,7 +660,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
     tc_profile_total(t_start);
 }
 
-template <int K, int CN, bool QA_TMEM>
+template <int K, int CN>
 static int launch_fused(const void* src, const void* flow, const void* logits, const void* gout, void* gsrc, void* gflow,
                         void* glogits, int B, int C, int Hs, int Ws, int H, int W, int accumulate, cudaStream_t st_) {
     static const PFN_tmapEncodeTiled enc = tmap_encoder();
@@ -688,7 +673,7 @@ static int launch_fused(const void* src, const void* flow, const void* logits, c
     const cuuint64_t sdim[4] = {(cuuint64_t)C, (cuuint64_t)Ws, (cuuint64_t)Hs, (cuuint64_t)B};
     const cuuint64_t sstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)Ws * C * 2, (cuuint64_t)Hs * Ws * C * 2};
     const cuuint32_t gbox[4] = {64, GW, GH, 1};                 // grad_out tile: 16 x 8 pixels
-    const cuuint32_t sbox[4] = {64, FB_BW, FB_QROWS, 1};        // source rows of one Q stage
+    const cuuint32_t sbox[4] = {64, FB_BW, FB_QROWS, 1};        // the source row of one Q stage
 
     // all three maps exist before anything is written (a failure here leaves the caller's buffers untouched)
     if (enc(&tg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(gout), odim, ostr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -703,17 +688,17 @@ static int launch_fused(const void* src, const void* flow, const void* logits, c
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return GFLA_E_NOTSUP;
         }
-    auto kern = k_local_attn_bwd_fused<K, CN, QA_TMEM>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemFB<CN, QA_TMEM>::ALLOC);
+    auto kern = k_local_attn_bwd_fused<K, CN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemFB<CN>::ALLOC);
     if (e != cudaSuccess) return static_cast<int>(e);
     if (!accumulate) {   // the reduce-adds need a zero-filled grad_source; nothing was written before this point
         const int z = zero_async(gsrc, (size_t)B * C * Hs * Ws * 2, st_);
         if (z != GFLA_OK) return z;
     }
     const int ngroups = B * ((H + GH - 1) / GH) * ((W + GW - 1) / GW);
-    kern<<<(unsigned)min(ngroups, sm_count()), FB_THREADS, SmemFB<CN, QA_TMEM>::ALLOC, st_>>>(
+    kern<<<(unsigned)min(ngroups, sm_count()), FB_THREADS, SmemFB<CN>::ALLOC, st_>>>(
         tg, ts, tgs, (const __nv_bfloat16*)src, (const float*)flow, (const __nv_bfloat16*)logits, (const __nv_bfloat16*)gout,
-        (__nv_bfloat16*)gsrc, (float*)gflow, (__nv_bfloat16*)glogits, B, C, Hs, Ws, H, W, accumulate);
+        (__nv_bfloat16*)gsrc, (float*)gflow, (__nv_bfloat16*)glogits, B, C, Hs, Ws, H, W, accumulate, tune_knob("GFLA_BWD_KNOBS", 0));
     return launch_status();
 }
 
@@ -729,11 +714,8 @@ bool local_attn_bwd_fused_supported(int C, int k, const void* src) {
 // other than the launch itself) and all three gradients are overwritten; 1: everything is added into the caller's buffers.
 int local_attn_bwd_fused_tc(const void* src, const void* flow, const void* logits, const void* gout, void* gsrc, void* gflow,
                             void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate, cudaStream_t st_) {
-    const bool qa_tmem = tc::tune_knob("GFLA_BWD_QA_TMEM", 0) != 0;      // experiment: A operand of the Q stages from TMEM
 #define GFLA_FB_CASE(K_, CN_) \
-    if (k == K_ && C == CN_) \
-        return qa_tmem ? tc::launch_fused<K_, CN_, true>(src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, accumulate, st_) \
-                       : tc::launch_fused<K_, CN_, false>(src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, accumulate, st_);
+    if (k == K_ && C == CN_) return tc::launch_fused<K_, CN_>(src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, accumulate, st_);
     GFLA_FB_CASE(5, 256) GFLA_FB_CASE(5, 128) GFLA_FB_CASE(5, 64)
     GFLA_FB_CASE(3, 256) GFLA_FB_CASE(3, 128) GFLA_FB_CASE(3, 64)
 #undef GFLA_FB_CASE

@@ -199,8 +199,11 @@ __device__ __forceinline__ bool fill_slab_row(uint32_t row, uint32_t swz, uint32
     constexpr int K1 = K + 1;
     const bool write = hit && r >= 0 && r <= K;
     if (!write && !(dirty & bit)) return false;
+    // zero the whole row; the 16-byte chunks go out in swizzled order: with rows of 64 (32) bytes, lanes 0, 2, 4, ... (0, 4, 8, ...)
+    // would otherwise hit the same 4 banks with the same chunk -- a 4-way conflict on every one of these stores, and they
+    // were 2/3 of all shared-memory store wavefronts of the forward kernel (ncu: l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st)
 #pragma unroll
-    for (int ch = 0; ch < BWT / 8; ++ch) sts128(row + ch * 16, 0u, 0u, 0u, 0u);
+    for (int ch = 0; ch < BWT / 8; ++ch) sts128(row + ((ch * 16) ^ swz), 0u, 0u, 0u, 0u);
     dirty &= ~bit;
     if (write) {
         dirty |= bit;
