@@ -73,7 +73,7 @@ struct SmemFB {
     static constexpr int OFF_QS = OFF_W + 36 * 128 * 2;
     static constexpr int OFF_INFO = OFF_QS + 128 * FB_QS_STRIDE;
     static constexpr int OFF_BAR = OFF_INFO + FB_NINFO * 32;
-    static constexpr int NBAR = 2 + 2 * NS + 2 * NQ + 2 * NA + 4 + FB_NINFO;
+    static constexpr int NBAR = 2 + 2 * NS + 2 * NQ + 2 * NA + 4 + 2 + FB_NINFO;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int ALLOC = OFF_TMEM + 16 + 1024;
     static constexpr int GS_COL0 = 256;                        // TMEM column of the first grad_source accumulator
@@ -91,7 +91,7 @@ __device__ __forceinline__ void fb_red_add_bf16x2(void* gptr, uint32_t v) {
 // register re-distribution between the warpgroups (all 4 warps of a warpgroup execute it; the CTA holds 512 x 128 registers)
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-constexpr int FB_REG_CTRL = 64, FB_REG_PIX = 176, FB_REG_FILL = 144, FB_REG_EPI = 128;   // sum = 512
+constexpr int FB_REG_CTRL = 64, FB_REG_PIX = 112, FB_REG_FILL = 208, FB_REG_EPI = 128;   // sum = 512
 static_assert(FB_REG_CTRL + FB_REG_PIX + FB_REG_FILL + FB_REG_EPI <= 512, "register budget");
 
 __device__ __forceinline__ float lds_f32(uint32_t a) {
@@ -107,7 +107,11 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                        const float* __restrict__ flow, const __nv_bfloat16* __restrict__ logits,
                        const __nv_bfloat16* __restrict__ gout, __nv_bfloat16* __restrict__ gsrc, float* __restrict__ gflow,
                        __nv_bfloat16* __restrict__ glogits, int B, int C, int Hs, int Ws, int H, int W, int accumulate, int knobs) {
-    // `knobs` (environment GFLA_BWD_KNOBS, default 0): bit 0 = also pull the next group's source rows into L2 ahead of time
+    // `knobs` (environment GFLA_BWD_KNOBS, default 0 = production): bit 0 = also pull the next group's source rows into L2 ahead of
+    // time.  Timing experiments (results are wrong when set): bit 1 pixel team skips the TMEM read / window picks, bit 2 gs epilogue
+    // skips staging + reduce-add, bit 3 builders skip the slab fills, bit 4 no Q MMAs, bit 5 no grad_source MMAs, bit 6 no source-row loads,
+    // bit 7 pixel team: no softmax / finalize / stores, bit 8 builders: no softmax / window, bit 9 gs epilogue: no irregular-pixel check and
+    // no TMEM reads, bit 10 no grad_out tile load / TMEM copy.
     using SM = SmemFB<CN>;
     constexpr int K1 = K + 1, KK = K * K, NS = SM::NS, NA = SM::NA, NH = SM::NH, HN = SM::HN, FB_NQ = SM::NQ;
     extern __shared__ uint8_t smem_raw[];
@@ -123,7 +127,9 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
     uint64_t* a_empty = a_full + NA;                 // [NA]
     uint64_t* gs_full = a_empty + NA;                // [2] grad_source accumulator half complete
     uint64_t* gs_empty = gs_full + 2;                // [2] 4 epilogue warps drained it
-    uint64_t* info_full = gs_empty + 2;              // [FB_NINFO]
+    uint64_t* qw_full = gs_empty + 2;                // the pixel team's 36 window dot products of a group sit in its staging rows
+    uint64_t* qw_empty = qw_full + 1;                // ... and have been read by the builders
+    uint64_t* info_full = qw_empty + 1;              // [FB_NINFO]
     FbInfo* infos = reinterpret_cast<FbInfo*>(smem + SM::OFF_INFO);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_TMEM);
 
@@ -140,6 +146,8 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         for (int i = 0; i < FB_NQ; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 4); }
         for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&gs_full[i], 1); mbar_init(&gs_empty[i], 4); }
+        mbar_init(qw_full, 128);
+        mbar_init(qw_empty, 128);
         for (int i = 0; i < FB_NINFO; ++i) mbar_init(&info_full[i], 1);
         fence_barrier_init();
         tma_prefetch_desc(&tmap_g);
@@ -186,7 +194,8 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             auto load_stage = [&](int s) {
                 const int cb = s / nrows, rc = s - cb * nrows, slot = it % NS;
                 mbar_wait(&s_empty[slot], ((it / NS) & 1) ^ 1, 0x000200 | slot, it);
-                if (elect_one()) {
+                if ((knobs & 64) && lane == 0) mbar_arrive(&s_full[slot]);
+                if (!(knobs & 64) && elect_one()) {
                     mbar_arrive_expect_tx(&s_full[slot], SM::S_STAGE);
 #pragma unroll
                     for (int cg = 0; cg < CN / 64; ++cg)
@@ -199,7 +208,8 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             int s = 0;
             for (; s < nst && s < NS; ++s) load_stage(s);
             mbar_wait(g_empty, (gi & 1) ^ 1, 0x000600, gi);
-            if (elect_one()) {
+            if ((knobs & 1024) && lane == 0) mbar_arrive(g_full);
+            if (!(knobs & 1024) && elect_one()) {
                 mbar_arrive_expect_tx(g_full, SM::G_BYTES);
 #pragma unroll
                 for (int cg = 0; cg < CN / 64; ++cg)
@@ -236,6 +246,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             tc_fence_after();
             if (elect_one()) {
                 // G[128 px][CN] -> TMEM, 16 channels (8 columns) per copy; ordered before the MMAs below, after those of the last group
+                if (!(knobs & 1024))
 #pragma unroll
                 for (int cg = 0; cg < CN / 64; ++cg)
 #pragma unroll
@@ -253,6 +264,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 if (elect_one()) {
                     const uint32_t b0 = smem_u32(smem + SM::OFF_S + slot * SM::S_STAGE);
                     const uint32_t d_tmem = tmem_base + buf * 32;
+                    if (!(knobs & 16))
 #pragma unroll
                     for (int cg = 0; cg < CN / 64; ++cg)
 #pragma unroll
@@ -287,6 +299,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                     if (elect_one()) {
                         const uint32_t a0 = smem_u32(smem + SM::OFF_A + st * SM::A_STAGE);
                         const uint32_t d_tmem = tmem_base + SM::GS_COL0 + buf * HN;
+                        if (!(knobs & 32))
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks) {   // 16 pixels per MMA
                             // A^T: M = positions (32 per slab, LBO = next slab), K = pixels (8 per 512-byte atom)
@@ -307,58 +320,40 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         }
       }   // warp 3: no role (it pads the control warpgroup so that setmaxnreg can hand its registers on)
     } else if (warp < 8) {
-        // ================================================================= pixel team: Q -> grad_flow, grad_logits
-        reg_inc<FB_REG_PIX>();
+        // ================================================================= pixel team: the (k+1)^2 window dot products Q of every pixel
+        // Extraction only: per Q stage TMEM -> thread-private staging row -> picks with dynamic shared addresses.  After the
+        // group's last stage the 36 values are left in the staging row (it is exactly 36 floats wide) for the builder thread
+        // of the same pixel, which owns the softmax and turns them into grad_logits / grad_flow: the per-pixel softmax,
+        // tap and softmax-backward arithmetic used to sit on this team's -- i.e. the Q chain's -- critical path (0.31 ms of 1.06).
+        reg_dec<FB_REG_PIX>();
         const int q = warp & 3, m = q * 32 + lane;
-        const float inv_kk = 1.0f / static_cast<float>(KK);
         const uint32_t qs_row = smem_u32(smem + SM::OFF_QS) + m * FB_QS_STRIDE;     // thread-private staging row
         uint32_t it = 0;
         int gi = 0;
-        // raw inputs of this thread's pixel, loaded one group ahead
-        __nv_bfloat16 lg[KK];
-        float pfx = 0.f, pfy = 0.f;
+        float pfx = 0.f, pfy = 0.f;          // flow of this thread's pixel, loaded one group ahead
         auto load_pixel = [&](int g) {
             const int px = (g % gxn) * GW + (m & 15), py = ((g / gxn) % gyn) * GH + (m >> 4), b = g / (gxn * gyn);
             if (px < W && py < H) {
                 const long long pofs = (long long)py * W + px;
-                const __nv_bfloat16* lp = logits + (long long)b * KK * hw + pofs;
-#pragma unroll
-                for (int t = 0; t < KK; ++t) lg[t] = lp[t * hw];
                 pfx = flow[(long long)b * 2 * hw + pofs];
                 pfy = flow[(long long)b * 2 * hw + hw + pofs];
             }
         };
         if (blockIdx.x < ngroups) load_pixel(blockIdx.x);
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
-            const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
+            const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH;
             const int px = gx0 + (m & 15), py = gy0 + (m >> 4);
-            const bool valid = px < W && py < H;
-            const long long pofs = (long long)py * W + px;
-            const long long tp0 = tc_profile_clock();
-            float p[KK];
-            float fx = 0.f, fy = 0.f;
-            bool regular = false;
-            int X0 = 0, Y0 = 0;
-            if (valid) {
-#pragma unroll
-                for (int t = 0; t < KK; ++t) p[t] = __bfloat162float(lg[t]);
-                softmax_inplace_f32<KK>(p);
-                fx = pfx;
-                fy = pfy;
-                AxisTap<float> tx[K], ty[K];
-                regular = taps_regular<K>(fx, fy, px, py, Hs, Ws, tx, ty);
-                X0 = tx[0].fl;
-                Y0 = ty[0].fl;
-            }
+            const bool live = px < W && py < H;      // irregular pixels are extracted too (their values are ignored by the builders)
+            // window origin = unclamped floor of the first tap (block_extractor_kernel.cu:62-66)
+            const int X0 = live ? axis_tap<float>(pfx, -(K / 2), px, Ws).fl : 0, Y0 = live ? axis_tap<float>(pfy, -(K / 2), py, Hs).fl : 0;
             if (g + (int)gridDim.x < ngroups) load_pixel(g + gridDim.x);
-            const bool live = valid && regular;
-            tc_profile_add(2, 6, tc_profile_clock() - tp0);          // softmax / taps of this group, raw loads of the next
             float Qw[K1 * K1];  // Q at the (clamped) window positions
 #pragma unroll
             for (int i = 0; i < K1 * K1; ++i) Qw[i] = 0.f;
 
             mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x020500, gi);
             const FbInfo inf = infos[gi % FB_NINFO];
+            mbar_wait(qw_empty, (gi & 1) ^ 1, 0x020600, gi);      // the builders have read the previous group's values out of the staging rows
             for (int cb = 0; cb < inf.ncb; ++cb) {
                 const int C0 = inf.x0 + cb * FB_BW;
                 for (int rc = 0; rc < inf.nrows; ++rc, ++it) {
@@ -372,7 +367,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                     }
                     const unsigned any = __ballot_sync(0xffffffffu, need);
                     mbar_wait(&q_full[buf], (it / FB_NQ) & 1, 0x020300 | buf, it);
-                    if (any != 0u) {
+                    if (any != 0u && !(knobs & 2)) {
                         tc_fence_after();
                         uint32_t v[32];
                         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 32, v);
@@ -397,16 +392,62 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                     if (lane == 0) mbar_arrive(&q_empty[buf]);
                 }
             }
-            // ---- finalize this pixel
+            // hand the window over: 36 floats = the whole staging row
+#pragma unroll
+            for (int i = 0; i < K1 * K1 / 4; ++i)
+                sts128(qs_row + i * 16, __float_as_uint(Qw[4 * i]), __float_as_uint(Qw[4 * i + 1]), __float_as_uint(Qw[4 * i + 2]), __float_as_uint(Qw[4 * i + 3]));
+            mbar_arrive(qw_full);
+        }
+    } else if (warp < 12) {
+        // ================================================================= builders (thread = pixel): softmax, taps, collapsed window,
+        // the weight slabs of every grad_source block -- and, one group later, the pixel's grad_logits / grad_flow from the window dot
+        // products the pixel team left in its staging row.  Order per group g: window(g) -> finalize(g-1) -> slabs(g): the window does
+        // not depend on the Q chain, so only the finalize sits between "Q chain of g-1 done" and "first slab of g".
+        reg_inc<FB_REG_FILL>();
+        const int q = warp & 3, m = q * 32 + lane;
+        const float inv_kk = 1.0f / static_cast<float>(KK);
+        const uint32_t wsm_a = smem_u32(smem + SM::OFF_W) + m * 4;
+        const uint32_t a_base = smem_u32(smem + SM::OFF_A) + m * (FB_BW * 2);
+        const uint32_t qs_row = smem_u32(smem + SM::OFF_QS) + m * FB_QS_STRIDE;     // the pixel team's staging row of this pixel
+        const uint32_t swz = ((m >> 1) & 3) << 4;   // 64B swizzle: 16B chunk ^= bits 1-2 of the row
+        uint32_t blk = 0, dirty = 0xffffffffu;
+        int gi = 0;
+        __nv_bfloat16 lg[KK];
+        float pfx = 0.f, pfy = 0.f;
+        auto load_pixel = [&](int g) {
+            const int px = (g % gxn) * GW + (m & 15), py = ((g / gxn) % gyn) * GH + (m >> 4), b = g / (gxn * gyn);
+            if (px < W && py < H) {
+                const long long pofs = (long long)py * W + px;
+                const __nv_bfloat16* lp = logits + (long long)b * KK * hw + pofs;
+#pragma unroll
+                for (int t = 0; t < KK; ++t) lg[t] = lp[t * hw];
+                pfx = flow[(long long)b * 2 * hw + pofs];
+                pfy = flow[(long long)b * 2 * hw + hw + pofs];
+            }
+        };
+        // state of the previous group's pixel, kept for its finalize
+        float pp[KK];
+        float fx_p = 0.f, fy_p = 0.f;
+        int px_p = 0, py_p = 0, b_p = 0;
+        bool valid_p = false, regular_p = false, have_p = false;
+        // grad_logits / grad_flow of the previous group's pixel (softmax backward; d/dflow as block_extractor_kernel.cu:163-168)
+        auto finalize = [&](int gip) {
             const long long tq0 = tc_profile_clock();
+            mbar_wait(qw_full, gip & 1, 0x030700, gip);
+            float Qw[K1 * K1];
+#pragma unroll
+            for (int i = 0; i < K1 * K1 / 4; ++i) lds128(qs_row + i * 16, Qw[4 * i], Qw[4 * i + 1], Qw[4 * i + 2], Qw[4 * i + 3]);
+            mbar_arrive(qw_empty);
+            if (knobs & 128) return;
+            const long long pofs = (long long)py_p * W + px_p;
             float dp[KK];
             float gfx = 0.f, gfy = 0.f;
-            if (live) {
+            if (valid_p && regular_p) {
                 AxisTap<float> tx[K], ty[K];
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
-                    tx[j] = axis_tap<float>(fx, j - K / 2, px, Ws);
-                    ty[j] = axis_tap<float>(fy, j - K / 2, py, Hs);
+                    tx[j] = axis_tap<float>(fx_p, j - K / 2, px_p, Ws);
+                    ty[j] = axis_tap<float>(fy_p, j - K / 2, py_p, Hs);
                 }
 #pragma unroll
                 for (int i = 0; i < K; ++i)
@@ -414,21 +455,21 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                     for (int j = 0; j < K; ++j) {
                         const float qLT = Qw[i * K1 + j], qRT = Qw[i * K1 + j + 1], qLB = Qw[(i + 1) * K1 + j], qRB = Qw[(i + 1) * K1 + j + 1];
                         dp[i * K + j] = inv_kk * (ty[i].wlo * (tx[j].wlo * qLT + tx[j].whi * qRT) + ty[i].whi * (tx[j].wlo * qLB + tx[j].whi * qRB));
-                        const float pij = p[i * K + j] * inv_kk;
+                        const float pij = pp[i * K + j] * inv_kk;
                         gfy += pij * (-tx[j].wlo * qLT - tx[j].whi * qRT + tx[j].wlo * qLB + tx[j].whi * qRB);
                         gfx += pij * (-ty[i].wlo * qLT - ty[i].whi * qLB + ty[i].wlo * qRT + ty[i].whi * qRB);
                     }
             }
             // irregular pixels: literal 4-tap dot products, the warp shares the channels of one pixel at a time
-            unsigned todo = __ballot_sync(0xffffffffu, valid && !regular);
+            unsigned todo = __ballot_sync(0xffffffffu, valid_p && !regular_p);
             while (todo) {
                 const int sl = __ffs(todo) - 1;
                 todo &= todo - 1;
-                const int qx = __shfl_sync(0xffffffffu, px, sl), qy = __shfl_sync(0xffffffffu, py, sl);
-                const float qfx = __shfl_sync(0xffffffffu, fx, sl), qfy = __shfl_sync(0xffffffffu, fy, sl);
+                const int qx = __shfl_sync(0xffffffffu, px_p, sl), qy = __shfl_sync(0xffffffffu, py_p, sl);
+                const float qfx = __shfl_sync(0xffffffffu, fx_p, sl), qfy = __shfl_sync(0xffffffffu, fy_p, sl);
                 const long long qofs = (long long)qy * W + qx;
-                const __nv_bfloat16* go = gout + ((long long)b * hw + qofs) * C;
-                const __nv_bfloat16* sb = src + (long long)b * Hs * Ws * C;
+                const __nv_bfloat16* go = gout + ((long long)b_p * hw + qofs) * C;
+                const __nv_bfloat16* sb = src + (long long)b_p * Hs * Ws * C;
                 float gx_acc = 0.f, gy_acc = 0.f;
 #pragma unroll
                 for (int i = 0; i < K; ++i) {
@@ -449,9 +490,9 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                             qLT += __shfl_xor_sync(0xffffffffu, qLT, o); qRT += __shfl_xor_sync(0xffffffffu, qRT, o);
                             qLB += __shfl_xor_sync(0xffffffffu, qLB, o); qRB += __shfl_xor_sync(0xffffffffu, qRB, o);
                         }
-                        if (lane == sl) {  // the owner keeps the results (its p[] is the right softmax)
+                        if (lane == sl) {  // the owner keeps the results (its pp[] is the right softmax)
                             dp[i * K + j] = inv_kk * (ayy.wlo * (axx.wlo * qLT + axx.whi * qRT) + ayy.whi * (axx.wlo * qLB + axx.whi * qRB));
-                            const float pij = p[i * K + j] * inv_kk;
+                            const float pij = pp[i * K + j] * inv_kk;
                             gy_acc += pij * (-axx.wlo * qLT - axx.whi * qRT + axx.wlo * qLB + axx.whi * qRB);
                             gx_acc += pij * (-ayy.wlo * qLT - ayy.whi * qLB + ayy.wlo * qRT + ayy.whi * qRB);
                         }
@@ -459,55 +500,32 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 }
                 if (lane == sl) { gfx = gx_acc; gfy = gy_acc; }
             }
-            if (valid) {
+            if (valid_p) {
                 float dot = 0.f;
 #pragma unroll
-                for (int t = 0; t < KK; ++t) dot += p[t] * dp[t];
-                __nv_bfloat16* gl = glogits + (long long)b * KK * hw + pofs;
+                for (int t = 0; t < KK; ++t) dot += pp[t] * dp[t];
+                __nv_bfloat16* gl = glogits + (long long)b_p * KK * hw + pofs;
 #pragma unroll
                 for (int t = 0; t < KK; ++t) {
-                    const float val = p[t] * (dp[t] - dot);
+                    const float val = pp[t] * (dp[t] - dot);
                     gl[t * hw] = __float2bfloat16_rn(accumulate ? __bfloat162float(gl[t * hw]) + val : val);
                 }
-                float* gf = gflow + (long long)b * 2 * hw + pofs;
+                float* gf = gflow + (long long)b_p * 2 * hw + pofs;
                 gf[0] = accumulate ? gf[0] + gfx : gfx;
                 gf[hw] = accumulate ? gf[hw] + gfy : gfy;
             }
-            tc_profile_add(2, 7, tc_profile_clock() - tq0);          // softmax backward, d/dflow, stores
-        }
-    } else if (warp < 12) {
-        // ================================================================= slab builders (thread = pixel)
-        reg_inc<FB_REG_FILL>();
-        const int q = warp & 3, m = q * 32 + lane;
-        const float inv_kk = 1.0f / static_cast<float>(KK);
-        const uint32_t wsm_a = smem_u32(smem + SM::OFF_W) + m * 4;
-        const uint32_t a_base = smem_u32(smem + SM::OFF_A) + m * (FB_BW * 2);
-        const uint32_t swz = ((m >> 1) & 3) << 4;   // 64B swizzle: 16B chunk ^= bits 1-2 of the row
-        uint32_t blk = 0, dirty = 0xffffffffu;
-        int gi = 0;
-        __nv_bfloat16 lg[KK];
-        float pfx = 0.f, pfy = 0.f;
-        auto load_pixel = [&](int g) {
-            const int px = (g % gxn) * GW + (m & 15), py = ((g / gxn) % gyn) * GH + (m >> 4), b = g / (gxn * gyn);
-            if (px < W && py < H) {
-                const long long pofs = (long long)py * W + px;
-                const __nv_bfloat16* lp = logits + (long long)b * KK * hw + pofs;
-#pragma unroll
-                for (int t = 0; t < KK; ++t) lg[t] = lp[t * hw];
-                pfx = flow[(long long)b * 2 * hw + pofs];
-                pfy = flow[(long long)b * 2 * hw + hw + pofs];
-            }
+            tc_profile_add(3, 7, tc_profile_clock() - tq0);          // wait for Q, softmax backward, d/dflow, stores
         };
         if (blockIdx.x < ngroups) load_pixel(blockIdx.x);
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
-            const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH;
+            const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
             const int px = gx0 + (m & 15), py = gy0 + (m >> 4);
             const bool valid = px < W && py < H;
             int X0 = 0, Y0 = 0;
             bool live = false;
             const long long tw0 = tc_profile_clock();
-            if (valid) {
-                float p[KK];
+            float p[KK];
+            if (valid && !(knobs & 256)) {
 #pragma unroll
                 for (int t = 0; t < KK; ++t) p[t] = __bfloat162float(lg[t]);
                 softmax_inplace_f32<KK>(p);
@@ -519,8 +537,10 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                     store_window_words<K>(wsm_a, w);
                 }
             }
-            if (g + (int)gridDim.x < ngroups) load_pixel(g + gridDim.x);
+            const float fx_c = pfx, fy_c = pfy;
+            if (g + (int)gridDim.x < ngroups && !(knobs & 256)) load_pixel(g + gridDim.x);
             tc_profile_add(3, 6, tc_profile_clock() - tw0);          // window of this group, raw loads of the next
+            if (have_p) finalize(gi - 1);
             mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x030500, gi);
             const FbInfo inf = infos[gi % FB_NINFO];
             const int nb4 = (inf.nrows + FB_GROWS - 1) / FB_GROWS;
@@ -533,15 +553,23 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                     const uint32_t a_stage = a_base + st * SM::A_STAGE;
                     const int R0 = inf.y0 + rb * FB_GROWS;
                     bool wrote = false;
+                    if (!(knobs & 8)) {
 #pragma unroll
                     for (int seg = 0; seg < FB_GROWS; ++seg)
                         wrote |= fill_slab_row<K, FB_BW>(a_stage + seg * FB_SLAB, swz, wsm_a, cols_hit, (R0 + seg) - Y0, e0, dirty,
                                                          1u << (st * FB_GROWS + seg));
+                    }
                     if (wrote) fence_proxy_async_smem();
                     mbar_arrive(&a_full[st]);
                 }
             }
+            // this group becomes the "previous" one
+#pragma unroll
+            for (int t = 0; t < KK; ++t) pp[t] = p[t];
+            fx_p = fx_c; fy_p = fy_c; px_p = px; py_p = py; b_p = b;
+            valid_p = valid; regular_p = live; have_p = true;
         }
+        if (have_p) finalize(gi - 1);
     } else {
         // ================================================================= grad_source epilogue (thread = position of the block)
         const int q = warp & 3, t = q * 32 + lane;          // block row t/32, column t%32 (as a PIXEL index for the irregular pass: 16 wide)
@@ -551,7 +579,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
             const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
             // ---- irregular pixels of this group (thread <-> pixel t): literal scatter, warp-cooperative
-            {
+            if (!(knobs & 512)) {
                 const int px = gx0 + (t & 15), py = gy0 + (t >> 4);
                 const bool valid = px < W && py < H;
                 bool regular = true;
@@ -617,14 +645,17 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
 #pragma unroll 1
                         for (int cg = 0; cg < HN / 64; ++cg, ++oi) {
                             uint32_t v0[32], v1[32];
+                            if (!(knobs & 512)) {
                             tmem_ld_32x32(taddr + cg * 64, v0);
                             tmem_ld_32x32(taddr + cg * 64 + 32, v1);
                             tmem_ld_wait();
+                            }
                             if (cg == HN / 64 - 1) {  // accumulator half fully read: hand it back to the MMA warp
                                 tc_fence_before();
                                 __syncwarp();
                                 if (lane == 0) mbar_arrive(&gs_empty[buf]);
                             }
+                            if (knobs & 4) continue;
                             const uint32_t ob = o_base + (oi & 1) * SM::O_BUF + lin * 128;
                             fb_named_bar_sync(1, 128);        // staging buffer (oi & 1) is free (issuer waited on its reader)
                             if (in_box) {

@@ -110,6 +110,9 @@ __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st
 __device__ __forceinline__ void sts16(uint32_t a, uint32_t v) {
     asm volatile("{\n\t.reg .b16 h;\n\tcvt.u16.u32 h, %1;\n\tst.shared.b16 [%0], h;\n\t}" ::"r"(a), "r"(v) : "memory");
 }
+__device__ __forceinline__ void lds128(uint32_t a, float& x, float& y, float& z, float& w) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(a) : "memory");
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
     uint32_t v;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
