@@ -441,16 +441,28 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
         const int q = warp & 3, m = q * 32 + lane;
         int ti = 0;
         {
+            // the flow of this thread's pixel is loaded one tile ahead (it only decides "regular or not"): taken on the spot it
+            // cost a full global-load latency at the head of every tile's epilogue
+            float nfx = 0.f, nfy = 0.f;
+            auto load_flow = [&](const TileIt& tl) {
+                const int px = tl.gx * GW + (m & 15), py = tl.ty * GH + (m >> 4);
+                if (px < W && py < H) {
+                    const long long o = (long long)tl.b * 2 * hw + (long long)py * W + px;
+                    nfx = flow[o];
+                    nfy = flow[o + hw];
+                }
+            };
+            TileIt nxt = first;
+            if (nxt.ok(geo)) { load_flow(nxt); nxt.next(geo, ustride); }
             for (TileIt cur = first; cur.ok(geo); cur.next(geo, ustride), ++ti) {
                 const int b = cur.b, gx = cur.gx, ty = cur.ty;
                 const int px = gx * GW + (m & 15), py = ty * GH + (m >> 4);
                 const bool valid = px < W && py < H;
                 const long long pofs = (long long)py * W + px;
                 bool regular = false;
-                float fx = 0.f, fy = 0.f;
+                const float fx = nfx, fy = nfy;
+                if (nxt.ok(geo)) { load_flow(nxt); nxt.next(geo, ustride); }
                 if (valid) {
-                    fx = flow[(long long)b * 2 * hw + pofs];
-                    fy = flow[(long long)b * 2 * hw + hw + pofs];
                     AxisTap<float> tx[K], ty_[K];
                     regular = taps_regular<K>(fx, fy, px, py, Hs, Ws, tx, ty_);
                 }
