@@ -39,7 +39,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 using namespace gfla;
 
 // which backward the automatic path takes where both can serve the call (GFLA_BWD_FUSED=0/1 overrides)
-constexpr bool kBwdFusedDefault = false;
+constexpr bool kBwdFusedDefault = true;
 
 #define REQ_PTR(p) do { if ((p) == nullptr) return GFLA_E_NULL; } while (0)
 #define REQ_ALIGN(p, dt) do { if (!aligned((p), elem_size(dt))) return GFLA_E_ALIGN; } while (0)

@@ -18,20 +18,22 @@
 //             as a TMA REDUCE-ADD box into grad_source (local_attn_bwd_tc.cu).  The accumulator is split into two
 //             channel halves so the epilogue drains one half while the tensor pipe fills the other.
 //
-// Warp roles (5 warpgroups, persistent CTA, static round-robin over pixel groups; setmaxnreg moves registers between them):
+// Warp roles (4 warpgroups, persistent CTA, static round-robin over pixel groups; setmaxnreg moves registers from the
+// control warpgroup to the builders):
 //   warp 0        producer: tap bounding box from the flow, TMA of the grad_out tile and of the source-row stages;
 //   warp 1        MMA issuer of the Q stages, warp 2 MMA issuer of the gs blocks (2 channel halves each);   (warp 3 idle)
 //   warps 4-7     Q extraction (thread = pixel): per Q stage TMEM -> thread-private shared-memory row -> picks its window
 //                 entries with DYNAMIC SHARED addresses (no dynamically indexed registers, hence no local-memory stack);
-//                 after the group's last stage the 36 values stay in the row for the finalize team;
-//   warps 8-11    slab builders (thread = pixel): softmax, taps, collapsed window, weight slabs of every gs block;
+//                 after the group's last stage the 36 values stay in the row for the builder thread of the same pixel;
+//   warps 8-11    builders (thread = pixel): softmax, taps, collapsed window, weight slabs of every gs block -- and, one group
+//                 later, softmax-backward and the d/dflow formula from the 36 window dot products -> grad_logits, grad_flow;
 //   warps 12-15   gs epilogue (thread = source position): TMEM -> bf16 -> swizzled staging -> TMA reduce-add;
-//                 irregular pixels (non-consecutive taps) are scattered here with vector reductions;
-//   warps 16-19   finalize (thread = pixel): softmax again, then softmax-backward and the d/dflow formula from the 36 window
-//                 dot products -> grad_logits, grad_flow.
-// The three pixel-level teams exist because the per-pixel arithmetic (about 2500 dependent instructions per pixel and group) is
-// what this kernel's time is made of once the data movement is pipelined (tools/ablate_bwd.py): on one team it serialises, and
-// when the finalize sat on the builders it also chained the grad_source pipeline of group g+1 behind the Q pipeline of group g.
+//                 irregular pixels (non-consecutive taps) are scattered here with vector reductions.
+// What the time is made of (tools/ablate_bwd.py, profiles/r2_bwd_ablation.md): with every load, MMA, fill and store switched
+// off, the barrier rings and schedule alone take a third of the kernel, and the per-pixel arithmetic (softmax, taps, window,
+// softmax backward: ~2500 dependent instructions per pixel and group on one or two warps per scheduler) another third; the
+// data movement and the tensor work hide behind them.  A fifth warpgroup for the finalize was tried and was slower (its register
+// budget has to come out of the other four: setmaxnreg only redistributes the launch allocation).
 // TMEM: 4 x 32 columns of Q accumulators, C/2 columns holding G as an MMA operand, 2 x C/2 (C = 64: 2 x 64) columns of
 // grad_source accumulators.  Shared-memory bandwidth (128 B/clk: MMA operand fetch + TMA + staging) is the resource this kernel
 // runs out of first (ncu: l1tex__data_pipe_{tc,lsu}_wavefronts_mem_shared); keeping G in TMEM removes the largest single reader.
@@ -45,7 +47,7 @@ constexpr int FB_QROWS = 1;          // source rows per Q stage (N = 32)
 constexpr int FB_GROWS = 4;          // source rows per gs block (M = 128)
 constexpr int FB_SLAB = 128 * FB_BW * 2;   // [128 pixels][32 positions] bf16, 64-byte rows, 64B swizzle
 constexpr int FB_NINFO = 8;
-constexpr int FB_THREADS = 640;       // 5 warpgroups: {producer, 2 MMA issuers, 1 idle}, Q extraction, slab builders, gs epilogue, finalize
+constexpr int FB_THREADS = 512;       // 4 warpgroups: {producer, MMA, 2 idle}, pixel team, slab builders, gs epilogue
 constexpr int FB_QS_STRIDE = 144;    // bytes per thread row of the Q staging (32 fp32 + 16: 16-byte stores of 8 lanes tile all banks)
 
 // schedule of one pixel group (32-byte slots): tap bounding box origin, column blocks, source rows, and the width (24 / 28 / 32
@@ -92,13 +94,11 @@ __device__ __forceinline__ void fb_named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ void fb_red_add_bf16x2(void* gptr, uint32_t v) {
     asm volatile("red.global.add.noftz.bf16x2 [%0], %1;" ::"l"(gptr), "r"(v) : "memory");
 }
-// register re-distribution between the warpgroups (all 4 warps of a warpgroup execute it; the CTA holds 65536 registers, the
-// kernel starts every thread at 96)
+// register re-distribution between the warpgroups (all 4 warps of a warpgroup execute it; the CTA holds 512 x 128 registers)
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-constexpr int FB_REG_CTRL = 40, FB_REG_PIX = 104, FB_REG_FILL = 144, FB_REG_EPI = 80, FB_REG_FIN = 112;
-// setmaxnreg only moves registers WITHIN the CTA's launch allocation (640 threads x 96): the five budgets must sum to 5 x 96
-static_assert(FB_REG_CTRL + FB_REG_PIX + FB_REG_FILL + FB_REG_EPI + FB_REG_FIN == 5 * 96, "register budget");
+constexpr int FB_REG_CTRL = 64, FB_REG_PIX = 112, FB_REG_FILL = 208, FB_REG_EPI = 128;   // sum = 512
+static_assert(FB_REG_CTRL + FB_REG_PIX + FB_REG_FILL + FB_REG_EPI <= 512, "register budget");
 
 __device__ __forceinline__ float lds_f32(uint32_t a) {
     float v;
@@ -331,7 +331,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         // group's last stage the 36 values are left in the staging row (it is exactly 36 floats wide) for the builder thread
         // of the same pixel, which owns the softmax and turns them into grad_logits / grad_flow: the per-pixel softmax,
         // tap and softmax-backward arithmetic used to sit on this team's -- i.e. the Q chain's -- critical path (0.31 ms of 1.06).
-        reg_inc<FB_REG_PIX>();
+        reg_dec<FB_REG_PIX>();
         const int q = warp & 3, m = q * 32 + lane;
         const uint32_t qs_row = smem_u32(smem + SM::OFF_QS) + m * FB_QS_STRIDE;     // thread-private staging row
         uint32_t it = 0;
@@ -406,12 +406,15 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         }
     } else if (warp < 12) {
         // ================================================================= builders (thread = pixel): softmax, taps, collapsed window,
-        // the weight slabs of every grad_source block
+        // the weight slabs of every grad_source block -- and, one group later, the pixel's grad_logits / grad_flow from the window dot
+        // products the pixel team left in its staging row.  Order per group g: window(g) -> finalize(g-1) -> slabs(g): the window does
+        // not depend on the Q chain, so only the finalize sits between "Q chain of g-1 done" and "first slab of g".
         reg_inc<FB_REG_FILL>();
         const int q = warp & 3, m = q * 32 + lane;
         const float inv_kk = 1.0f / static_cast<float>(KK);
         const uint32_t wsm_a = smem_u32(smem + SM::OFF_W) + m * 4;
         const uint32_t a_base = smem_u32(smem + SM::OFF_A) + m * (FB_BW * 2);
+        const uint32_t qs_row = smem_u32(smem + SM::OFF_QS) + m * FB_QS_STRIDE;     // the pixel team's staging row of this pixel
         const uint32_t swz = ((m >> 1) & 3) << 4;   // 64B swizzle: 16B chunk ^= bits 1-2 of the row
         uint32_t blk = 0, dirty = 0xffffffffu;
         int gi = 0;
@@ -427,6 +430,97 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 pfx = flow[(long long)b * 2 * hw + pofs];
                 pfy = flow[(long long)b * 2 * hw + hw + pofs];
             }
+        };
+        // state of the previous group's pixel, kept for its finalize
+        float pp[KK];
+        float fx_p = 0.f, fy_p = 0.f;
+        int px_p = 0, py_p = 0, b_p = 0;
+        bool valid_p = false, regular_p = false, have_p = false;
+        // grad_logits / grad_flow of the previous group's pixel (softmax backward; d/dflow as block_extractor_kernel.cu:163-168)
+        auto finalize = [&](int gip) {
+            const long long tq0 = tc_profile_clock();
+            mbar_wait(qw_full, gip & 1, 0x030700, gip);
+            float Qw[K1 * K1];
+#pragma unroll
+            for (int i = 0; i < K1 * K1 / 4; ++i) lds128(qs_row + i * 16, Qw[4 * i], Qw[4 * i + 1], Qw[4 * i + 2], Qw[4 * i + 3]);
+            mbar_arrive(qw_empty);
+            if (knobs & 128) return;
+            const long long pofs = (long long)py_p * W + px_p;
+            float dp[KK];
+            float gfx = 0.f, gfy = 0.f;
+            if (valid_p && regular_p) {
+                AxisTap<float> tx[K], ty[K];
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    tx[j] = axis_tap<float>(fx_p, j - K / 2, px_p, Ws);
+                    ty[j] = axis_tap<float>(fy_p, j - K / 2, py_p, Hs);
+                }
+#pragma unroll
+                for (int i = 0; i < K; ++i)
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        const float qLT = Qw[i * K1 + j], qRT = Qw[i * K1 + j + 1], qLB = Qw[(i + 1) * K1 + j], qRB = Qw[(i + 1) * K1 + j + 1];
+                        dp[i * K + j] = inv_kk * (ty[i].wlo * (tx[j].wlo * qLT + tx[j].whi * qRT) + ty[i].whi * (tx[j].wlo * qLB + tx[j].whi * qRB));
+                        const float pij = pp[i * K + j] * inv_kk;
+                        gfy += pij * (-tx[j].wlo * qLT - tx[j].whi * qRT + tx[j].wlo * qLB + tx[j].whi * qRB);
+                        gfx += pij * (-ty[i].wlo * qLT - ty[i].whi * qLB + ty[i].wlo * qRT + ty[i].whi * qRB);
+                    }
+            }
+            // irregular pixels: literal 4-tap dot products, the warp shares the channels of one pixel at a time
+            unsigned todo = __ballot_sync(0xffffffffu, valid_p && !regular_p);
+            while (todo) {
+                const int sl = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int qx = __shfl_sync(0xffffffffu, px_p, sl), qy = __shfl_sync(0xffffffffu, py_p, sl);
+                const float qfx = __shfl_sync(0xffffffffu, fx_p, sl), qfy = __shfl_sync(0xffffffffu, fy_p, sl);
+                const long long qofs = (long long)qy * W + qx;
+                const __nv_bfloat16* go = gout + ((long long)b_p * hw + qofs) * C;
+                const __nv_bfloat16* sb = src + (long long)b_p * Hs * Ws * C;
+                float gx_acc = 0.f, gy_acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    const AxisTap<float> ayy = axis_tap<float>(qfy, i - K / 2, qy, Hs);
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        const AxisTap<float> axx = axis_tap<float>(qfx, j - K / 2, qx, Ws);
+                        float qLT = 0.f, qRT = 0.f, qLB = 0.f, qRB = 0.f;
+                        for (int c = lane; c < C; c += 32) {
+                            const float gv = __bfloat162float(go[c]);
+                            qLT += gv * __bfloat162float(sb[((long long)ayy.lo * Ws + axx.lo) * C + c]);
+                            qRT += gv * __bfloat162float(sb[((long long)ayy.lo * Ws + axx.hi) * C + c]);
+                            qLB += gv * __bfloat162float(sb[((long long)ayy.hi * Ws + axx.lo) * C + c]);
+                            qRB += gv * __bfloat162float(sb[((long long)ayy.hi * Ws + axx.hi) * C + c]);
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            qLT += __shfl_xor_sync(0xffffffffu, qLT, o); qRT += __shfl_xor_sync(0xffffffffu, qRT, o);
+                            qLB += __shfl_xor_sync(0xffffffffu, qLB, o); qRB += __shfl_xor_sync(0xffffffffu, qRB, o);
+                        }
+                        if (lane == sl) {  // the owner keeps the results (its pp[] is the right softmax)
+                            dp[i * K + j] = inv_kk * (ayy.wlo * (axx.wlo * qLT + axx.whi * qRT) + ayy.whi * (axx.wlo * qLB + axx.whi * qRB));
+                            const float pij = pp[i * K + j] * inv_kk;
+                            gy_acc += pij * (-axx.wlo * qLT - axx.whi * qRT + axx.wlo * qLB + axx.whi * qRB);
+                            gx_acc += pij * (-ayy.wlo * qLT - ayy.whi * qLB + ayy.wlo * qRT + ayy.whi * qRB);
+                        }
+                    }
+                }
+                if (lane == sl) { gfx = gx_acc; gfy = gy_acc; }
+            }
+            if (valid_p) {
+                float dot = 0.f;
+#pragma unroll
+                for (int t = 0; t < KK; ++t) dot += pp[t] * dp[t];
+                __nv_bfloat16* gl = glogits + (long long)b_p * KK * hw + pofs;
+#pragma unroll
+                for (int t = 0; t < KK; ++t) {
+                    const float val = pp[t] * (dp[t] - dot);
+                    gl[t * hw] = __float2bfloat16_rn(accumulate ? __bfloat162float(gl[t * hw]) + val : val);
+                }
+                float* gf = gflow + (long long)b_p * 2 * hw + pofs;
+                gf[0] = accumulate ? gf[0] + gfx : gfx;
+                gf[hw] = accumulate ? gf[hw] + gfy : gfy;
+            }
+            tc_profile_add(3, 7, tc_profile_clock() - tq0);          // wait for Q, softmax backward, d/dflow, stores
         };
         if (blockIdx.x < ngroups) load_pixel(blockIdx.x);
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
@@ -449,8 +543,10 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                     store_window_words<K>(wsm_a, w);
                 }
             }
+            const float fx_c = pfx, fy_c = pfy;
             if (g + (int)gridDim.x < ngroups && !(knobs & 256)) load_pixel(g + gridDim.x);
             tc_profile_add(3, 6, tc_profile_clock() - tw0);          // window of this group, raw loads of the next
+            if (have_p) finalize(gi - 1);
             mbar_wait(&info_full[gi % FB_NINFO], (gi / FB_NINFO) & 1, 0x030500, gi);
             const FbInfo inf = infos[gi % FB_NINFO];
             const int nb4 = (inf.nrows + FB_GROWS - 1) / FB_GROWS;
@@ -473,10 +569,15 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                     mbar_arrive(&a_full[st]);
                 }
             }
+            // this group becomes the "previous" one
+#pragma unroll
+            for (int t = 0; t < KK; ++t) pp[t] = p[t];
+            fx_p = fx_c; fy_p = fy_c; px_p = px; py_p = py; b_p = b;
+            valid_p = valid; regular_p = live; have_p = true;
         }
-    } else if (warp < 16) {
+        if (have_p) finalize(gi - 1);
+    } else {
         // ================================================================= grad_source epilogue (thread = position of the block)
-        reg_dec<FB_REG_EPI>();
         const int q = warp & 3, t = q * 32 + lane;          // block row t/32, column t%32 (as a PIXEL index for the irregular pass: 16 wide)
         const uint32_t o_base = smem_u32(smem + SM::OFF_O);
         uint32_t u = 0, oi = 0;   // oi: running index of the staging tile (alternates between the two buffers)
@@ -549,35 +650,33 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + SM::GS_COL0 + buf * HN;
 #pragma unroll 1
                         for (int cg = 0; cg < HN / 64; ++cg, ++oi) {
-                            const uint32_t ob = o_base + (oi & 1) * SM::O_BUF + lin * 128;
-                            if (!(knobs & 4)) fb_named_bar_sync(1, 128);   // staging buffer (oi & 1) is free (issuer waited on its reader)
-#pragma unroll
-                            for (int hh = 0; hh < 2; ++hh) {  // 32 accumulator columns (channels) per round: half the registers of a 64-column read
-                                uint32_t v[32];
-                                if (!(knobs & 512)) {
-                                    tmem_ld_32x32(taddr + cg * 64 + hh * 32, v);
-                                    tmem_ld_wait();
-                                }
-                                if (cg == HN / 64 - 1 && hh == 1) {  // accumulator half fully read: hand it back to the MMA warp
-                                    tc_fence_before();
-                                    __syncwarp();
-                                    if (lane == 0) mbar_arrive(&gs_empty[buf]);
-                                }
-                                if (in_box && !(knobs & 4)) {
-#pragma unroll
-                                    for (int c4 = 0; c4 < 4; ++c4) {  // 4 x 16 bytes = 32 channels, 128B swizzle (chunk ^= row & 7)
-                                        const int ch = hh * 4 + c4;
-                                        uint32_t pk[4];
-#pragma unroll
-                                        for (int i = 0; i < 4; ++i) {
-                                            const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[8 * c4 + 2 * i]), __uint_as_float(v[8 * c4 + 2 * i + 1]));
-                                            pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
-                                        }
-                                        sts128(ob + ((ch ^ (lin & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
-                                    }
-                                }
+                            uint32_t v0[32], v1[32];
+                            if (!(knobs & 512)) {
+                            tmem_ld_32x32(taddr + cg * 64, v0);
+                            tmem_ld_32x32(taddr + cg * 64 + 32, v1);
+                            tmem_ld_wait();
+                            }
+                            if (cg == HN / 64 - 1) {  // accumulator half fully read: hand it back to the MMA warp
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&gs_empty[buf]);
                             }
                             if (knobs & 4) continue;
+                            const uint32_t ob = o_base + (oi & 1) * SM::O_BUF + lin * 128;
+                            fb_named_bar_sync(1, 128);        // staging buffer (oi & 1) is free (issuer waited on its reader)
+                            if (in_box) {
+#pragma unroll
+                            for (int ch = 0; ch < 8; ++ch) {  // 8 x 16 bytes = 64 channels, 128B swizzle (chunk ^= row & 7)
+                                const uint32_t* v = ch < 4 ? v0 + 8 * ch : v1 + 8 * (ch - 4);
+                                uint32_t pk[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                                    pk[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                                }
+                                sts128(ob + ((ch ^ (lin & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+                            }
+                            }
                             fence_proxy_async_smem();
                             fb_named_bar_sync(2, 128);        // tile complete
                             if (warp == 12 && elect_one()) {
@@ -591,132 +690,6 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 }
         }
         if (warp == 12 && elect_one()) bulk_wait<0>();
-    } else {
-        // ================================================================= finalize (thread = pixel): grad_logits / grad_flow of every pixel
-        // from the window dot products the extraction team leaves in its staging row (softmax backward; d/dflow as
-        // block_extractor_kernel.cu:163-168).  Own team: see the header.
-        reg_inc<FB_REG_FIN>();
-        const int q = warp & 3, m = q * 32 + lane;
-        const float inv_kk = 1.0f / static_cast<float>(KK);
-        const uint32_t qs_row = smem_u32(smem + SM::OFF_QS) + m * FB_QS_STRIDE;     // the extraction team's staging row of this pixel
-        int gi = 0;
-        __nv_bfloat16 lg[KK];
-        float pfx = 0.f, pfy = 0.f;
-        auto load_pixel = [&](int g) {
-            const int px = (g % gxn) * GW + (m & 15), py = ((g / gxn) % gyn) * GH + (m >> 4), b = g / (gxn * gyn);
-            if (px < W && py < H) {
-                const long long pofs = (long long)py * W + px;
-                const __nv_bfloat16* lp = logits + (long long)b * KK * hw + pofs;
-#pragma unroll
-                for (int t = 0; t < KK; ++t) lg[t] = lp[t * hw];
-                pfx = flow[(long long)b * 2 * hw + pofs];
-                pfy = flow[(long long)b * 2 * hw + hw + pofs];
-            }
-        };
-        if (blockIdx.x < ngroups) load_pixel(blockIdx.x);
-        for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
-            const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
-            const int px = gx0 + (m & 15), py = gy0 + (m >> 4);
-            const bool valid = px < W && py < H;
-            float p[KK];
-            float fx = 0.f, fy = 0.f;
-            bool regular = false;
-            if (valid && !(knobs & 128)) {
-#pragma unroll
-                for (int t = 0; t < KK; ++t) p[t] = __bfloat162float(lg[t]);
-                softmax_inplace_f32<KK>(p);
-                fx = pfx;
-                fy = pfy;
-                AxisTap<float> tx0[K], ty0[K];
-                regular = taps_regular<K>(fx, fy, px, py, Hs, Ws, tx0, ty0);
-            }
-            const long long tq0 = tc_profile_clock();
-            mbar_wait(qw_full, gi & 1, 0x060700, gi);
-            float Qw[K1 * K1];
-#pragma unroll
-            for (int i = 0; i < K1 * K1 / 4; ++i) lds128(qs_row + i * 16, Qw[4 * i], Qw[4 * i + 1], Qw[4 * i + 2], Qw[4 * i + 3]);
-            mbar_arrive(qw_empty);
-            if (knobs & 128) continue;
-            const long long pofs = (long long)py * W + px;
-            float dp[KK];
-            float gfx = 0.f, gfy = 0.f;
-            if (valid && regular) {
-                AxisTap<float> tx[K], ty[K];
-#pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    tx[j] = axis_tap<float>(fx, j - K / 2, px, Ws);
-                    ty[j] = axis_tap<float>(fy, j - K / 2, py, Hs);
-                }
-#pragma unroll
-                for (int i = 0; i < K; ++i)
-#pragma unroll
-                    for (int j = 0; j < K; ++j) {
-                        const float qLT = Qw[i * K1 + j], qRT = Qw[i * K1 + j + 1], qLB = Qw[(i + 1) * K1 + j], qRB = Qw[(i + 1) * K1 + j + 1];
-                        dp[i * K + j] = inv_kk * (ty[i].wlo * (tx[j].wlo * qLT + tx[j].whi * qRT) + ty[i].whi * (tx[j].wlo * qLB + tx[j].whi * qRB));
-                        const float pij = p[i * K + j] * inv_kk;
-                        gfy += pij * (-tx[j].wlo * qLT - tx[j].whi * qRT + tx[j].wlo * qLB + tx[j].whi * qRB);
-                        gfx += pij * (-ty[i].wlo * qLT - ty[i].whi * qLB + ty[i].wlo * qRT + ty[i].whi * qRB);
-                    }
-            }
-            // irregular pixels: literal 4-tap dot products, the warp shares the channels of one pixel at a time
-            unsigned todo = __ballot_sync(0xffffffffu, valid && !regular);
-            while (todo) {
-                const int sl = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const int qx = __shfl_sync(0xffffffffu, px, sl), qy = __shfl_sync(0xffffffffu, py, sl);
-                const float qfx = __shfl_sync(0xffffffffu, fx, sl), qfy = __shfl_sync(0xffffffffu, fy, sl);
-                const long long qofs = (long long)qy * W + qx;
-                const __nv_bfloat16* go = gout + ((long long)b * hw + qofs) * C;
-                const __nv_bfloat16* sb = src + (long long)b * Hs * Ws * C;
-                float gx_acc = 0.f, gy_acc = 0.f;
-#pragma unroll
-                for (int i = 0; i < K; ++i) {
-                    const AxisTap<float> ayy = axis_tap<float>(qfy, i - K / 2, qy, Hs);
-#pragma unroll
-                    for (int j = 0; j < K; ++j) {
-                        const AxisTap<float> axx = axis_tap<float>(qfx, j - K / 2, qx, Ws);
-                        float qLT = 0.f, qRT = 0.f, qLB = 0.f, qRB = 0.f;
-                        for (int c = lane; c < C; c += 32) {
-                            const float gv = __bfloat162float(go[c]);
-                            qLT += gv * __bfloat162float(sb[((long long)ayy.lo * Ws + axx.lo) * C + c]);
-                            qRT += gv * __bfloat162float(sb[((long long)ayy.lo * Ws + axx.hi) * C + c]);
-                            qLB += gv * __bfloat162float(sb[((long long)ayy.hi * Ws + axx.lo) * C + c]);
-                            qRB += gv * __bfloat162float(sb[((long long)ayy.hi * Ws + axx.hi) * C + c]);
-                        }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            qLT += __shfl_xor_sync(0xffffffffu, qLT, o); qRT += __shfl_xor_sync(0xffffffffu, qRT, o);
-                            qLB += __shfl_xor_sync(0xffffffffu, qLB, o); qRB += __shfl_xor_sync(0xffffffffu, qRB, o);
-                        }
-                        if (lane == sl) {  // the owner keeps the results (its p[] is the right softmax)
-                            dp[i * K + j] = inv_kk * (ayy.wlo * (axx.wlo * qLT + axx.whi * qRT) + ayy.whi * (axx.wlo * qLB + axx.whi * qRB));
-                            const float pij = p[i * K + j] * inv_kk;
-                            gy_acc += pij * (-axx.wlo * qLT - axx.whi * qRT + axx.wlo * qLB + axx.whi * qRB);
-                            gx_acc += pij * (-ayy.wlo * qLT - ayy.whi * qLB + ayy.wlo * qRT + ayy.whi * qRB);
-                        }
-                    }
-                }
-                if (lane == sl) { gfx = gx_acc; gfy = gy_acc; }
-            }
-            if (valid) {
-                float dot = 0.f;
-#pragma unroll
-                for (int t = 0; t < KK; ++t) dot += p[t] * dp[t];
-                __nv_bfloat16* gl = glogits + (long long)b * KK * hw + pofs;
-#pragma unroll
-                for (int t = 0; t < KK; ++t) {
-                    const float val = p[t] * (dp[t] - dot);
-                    gl[t * hw] = __float2bfloat16_rn(accumulate ? __bfloat162float(gl[t * hw]) + val : val);
-                }
-                float* gf = gflow + (long long)b * 2 * hw + pofs;
-                gf[0] = accumulate ? gf[0] + gfx : gfx;
-                gf[hw] = accumulate ? gf[hw] + gfy : gfy;
-            }
-            tc_profile_add(6, 7, tc_profile_clock() - tq0);          // wait for Q, softmax backward, d/dflow, stores
-            // raw inputs of the next group only now (this team waits for the Q chain anyway; holding them across the arithmetic
-            // above would not fit its register budget)
-            if (g + (int)gridDim.x < ngroups && !(knobs & 128)) load_pixel(g + gridDim.x);
-        }
     }
     tc_fence_before();
     __syncthreads();

@@ -41,7 +41,7 @@ if a.which == 2:
              1: {0: "source stage landed", 4: "Q acc drained", 5: "info", 7: "G landed"},
              5: {1: "slabs built", 5: "info", 6: "gs acc drained", 7: "G landed"},
              2: {3: "Q acc full", 5: "info", 6: "[busy] softmax/taps + next loads", 7: "[busy] finalize"},
-             3: {2: "slab stage free", 5: "info", 6: "[busy] window build"},
+             3: {2: "slab stage free", 5: "info", 6: "[busy] window build", 7: "[busy + wait for Q] finalize of the previous group"},
              4: {3: "gs acc full", 5: "info"}}
 else:
     names = {0: ("producer", 1), 1: ("mma", 1), 2: ("builders(x8)" if a.which == 1 else "builders(x4)", 8 if a.which == 1 else 4), 3: ("epilogue(x4)", 4)}
