@@ -36,6 +36,8 @@ SIGNATURES = {
     "gfla_local_attn_fwd": [_vp] * 5 + [_i] * 11 + [_vp],
     "gfla_local_attn_blend_fwd": [_vp] * 6 + [_i] * 11 + [_vp],
     "gfla_local_attn_bwd": [_vp] * 7 + [_i] * 12 + [_vp],
+    "gfla_local_attn_bwd_workspace_bytes": [_i],
+    "gfla_local_attn_bwd_ws": [_vp] * 7 + [_i] * 12 + [_vp, ctypes.c_longlong, _vp],
 }
 
 _lib = None
@@ -58,6 +60,7 @@ def lib() -> ctypes.CDLL:
             fn.argtypes = argtypes
             fn.restype = _i
         l.gfla_debug_launch_count.restype = ctypes.c_ulonglong
+        l.gfla_local_attn_bwd_workspace_bytes.restype = ctypes.c_longlong
         l.gfla_error_string.argtypes = [_i]
         l.gfla_error_string.restype = ctypes.c_char_p
         if l.gfla_abi_version() != ABI_VERSION:

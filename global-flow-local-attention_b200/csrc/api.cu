@@ -16,7 +16,7 @@ bool local_attn_bwd_tc_supported(int C, int k, int dtype, int flow_dtype, int la
 bool local_attn_bwd_q_tc_supported(int C, int k);
 int local_attn_bwd_q_tc(const void* src, const void* flow, const void* logits, const void* gout, void* gflow, void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate, cudaStream_t);
 bool local_attn_bwd_fused_supported(int C, int k, const void* src);
-int local_attn_bwd_fused_tc(const void* src, const void* flow, const void* logits, const void* gout, void* gsrc, void* gflow, void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate, cudaStream_t);
+int local_attn_bwd_fused_tc(const void* src, const void* flow, const void* logits, const void* gout, void* gsrc, void* gflow, void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate, void* workspace, long long workspace_bytes, cudaStream_t);
 int local_attn_bwd_gs_tc(const void* flow, const void* logits, const void* gout, void* gsrc, int B, int C, int Hs, int Ws, int H, int W, int k, cudaStream_t);
 int local_attn_fwd_tc(const void*, const void*, const void*, void*, void*, const void*, const void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 int relayout(const void*, void*, int, int, int, int, int, int, cudaStream_t);
@@ -198,9 +198,10 @@ int gfla_local_attn_blend_fwd(const void* source, const void* flow, const void* 
                               algo, stream);
 }
 
-int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits, const void* grad_out,
-                        void* grad_source, void* grad_flow, void* grad_logits, int B, int C, int Hs, int Ws, int H, int W,
-                        int k, int dtype, int flow_dtype, int layout, int accumulate, int algo, gfla_stream_t stream) {
+static int local_attn_bwd_any(const void* source, const void* flow, const void* logits, const void* grad_out,
+                              void* grad_source, void* grad_flow, void* grad_logits, int B, int C, int Hs, int Ws, int H, int W,
+                              int k, int dtype, int flow_dtype, int layout, int accumulate, int algo, void* workspace,
+                              long long workspace_bytes, gfla_stream_t stream) {
     if (layout != GFLA_NCHW && layout != GFLA_NHWC) return GFLA_E_SHAPE;
     REQ_PTR(source); REQ_PTR(flow); REQ_PTR(logits); REQ_PTR(grad_out); REQ_PTR(grad_source); REQ_PTR(grad_flow); REQ_PTR(grad_logits);
     if (!pos(B) || !pos(C) || !pos(Hs) || !pos(Ws) || !pos(H) || !pos(W) || k < 1 || k > 9) return GFLA_E_SHAPE;
@@ -240,7 +241,8 @@ int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits
             char* gl_ = (char*)grad_logits + b0 * per_l;
             int e = GFLA_OK;
             if (fused) {
-                e = local_attn_bwd_fused_tc(s_, f_, l_, g_, gs_, gf_, gl_, nb, C, Hs, Ws, H, W, k, accumulate, (cudaStream_t)stream);
+                e = local_attn_bwd_fused_tc(s_, f_, l_, g_, gs_, gf_, gl_, nb, C, Hs, Ws, H, W, k, accumulate, workspace, workspace_bytes,
+                                            (cudaStream_t)stream);
                 if (e != GFLA_OK) return e;
                 continue;
             }
@@ -258,6 +260,24 @@ int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits
     }
     return local_attn_bwd_gather(source, flow, logits, grad_out, grad_source, grad_flow, grad_logits, B, C, Hs, Ws, H, W,
                                  k, dtype, flow_dtype, accumulate, layout, /*do_gs=*/1, (cudaStream_t)stream);
+}
+
+int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits, const void* grad_out,
+                        void* grad_source, void* grad_flow, void* grad_logits, int B, int C, int Hs, int Ws, int H, int W,
+                        int k, int dtype, int flow_dtype, int layout, int accumulate, int algo, gfla_stream_t stream) {
+    return local_attn_bwd_any(source, flow, logits, grad_out, grad_source, grad_flow, grad_logits, B, C, Hs, Ws, H, W, k, dtype,
+                              flow_dtype, layout, accumulate, algo, nullptr, 0, stream);
+}
+
+long long gfla_local_attn_bwd_workspace_bytes(int B) { return B > 0 ? 4LL * B : 0; }
+
+int gfla_local_attn_bwd_ws(const void* source, const void* flow, const void* logits, const void* grad_out,
+                           void* grad_source, void* grad_flow, void* grad_logits, int B, int C, int Hs, int Ws, int H, int W,
+                           int k, int dtype, int flow_dtype, int layout, int accumulate, int algo, void* workspace,
+                           long long workspace_bytes, gfla_stream_t stream) {
+    if (workspace != nullptr && workspace_bytes < 0) return GFLA_E_SHAPE;
+    return local_attn_bwd_any(source, flow, logits, grad_out, grad_source, grad_flow, grad_logits, B, C, Hs, Ws, H, W, k, dtype,
+                              flow_dtype, layout, accumulate, algo, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -81,7 +81,7 @@ struct SmemFB {
     static constexpr int OFF_BAR = OFF_INFO + FB_NINFO * 32;
     static constexpr int NBAR = 2 + 2 * NS + 2 * NQ + 2 * NA + 4 + 2 + FB_NINFO;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
-    static constexpr int ALLOC = OFF_TMEM + 16 + 1024;
+    static constexpr int ALLOC = OFF_TMEM + 16 + 1024;      // OFF_TMEM + 0: TMEM base address, + 4: sample the producer is working on
     static constexpr int GS_COL0 = 256;                        // TMEM column of the first grad_source accumulator
 };
 static_assert(SmemFB<256>::ALLOC <= 232448, "shared memory budget");
@@ -112,7 +112,13 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                        const __grid_constant__ FbReduceMaps tmaps_gs, const __nv_bfloat16* __restrict__ src,
                        const float* __restrict__ flow, const __nv_bfloat16* __restrict__ logits,
                        const __nv_bfloat16* __restrict__ gout, __nv_bfloat16* __restrict__ gsrc, float* __restrict__ gflow,
-                       __nv_bfloat16* __restrict__ glogits, int B, int C, int Hs, int Ws, int H, int W, int accumulate, int knobs) {
+                       __nv_bfloat16* __restrict__ glogits, int B, int C, int Hs, int Ws, int H, int W, int accumulate, int knobs,
+                       unsigned int* __restrict__ zero_flags) {
+    // zero_flags != nullptr: grad_source arrives UNINITIALISED and is zero-filled here, sample by sample, by the otherwise idle
+    // warp 3 of every CTA, at most two samples ahead of the CTA's own progress (so the zeros are still in L2 when the
+    // reduce-adds land on them and reach HBM once); zero_flags[b] counts the CTAs that have finished their slice of sample b
+    // and the epilogue waits for all of them before its first add into a sample.  All CTAs are co-resident (grid <= SM count,
+    // one CTA per SM), and a CTA's zeroing never waits for another CTA, so the wait cannot deadlock.
     // `knobs` (environment GFLA_BWD_KNOBS, default 0 = production): bit 0 = also pull the next group's source rows into L2 ahead of
     // time.  Timing experiments (results are wrong when set): bit 1 pixel team skips the TMEM read / window picks, bit 2 gs epilogue
     // skips staging + reduce-add, bit 3 builders skip the slab fills, bit 4 no Q MMAs, bit 5 no grad_source MMAs, bit 6 no source-row loads,
@@ -138,6 +144,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
     uint64_t* info_full = qw_empty + 1;              // [FB_NINFO]
     FbInfo* infos = reinterpret_cast<FbInfo*>(smem + SM::OFF_INFO);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_TMEM);
+    volatile int* cur_sample = reinterpret_cast<volatile int*>(smem + SM::OFF_TMEM + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long t_start = tc_profile_clock();
@@ -146,6 +153,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
     const long long hw = (long long)H * W;
 
     if (threadIdx.x == 0) {
+        *cur_sample = 0;
         mbar_init(g_full, 1);
         mbar_init(g_empty, 2);      // one commit from each MMA-issuing warp
         for (int i = 0; i < NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
@@ -187,6 +195,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
             const int ncb = (x1 - x0 + FB_BW) / FB_BW, nrows = y1 - y0 + 1, nst = ncb * nrows;
             if (lane == 0) {
+                *cur_sample = b;
                 const int wl = x1 - (x0 + FB_BW * (ncb - 1)) + 1;
                 infos[gi % FB_NINFO] = FbInfo{x0, y0, ncb, nrows, wl <= 24 ? 24 : (wl <= 28 ? 28 : 32), 0, 0, 0};
                 mbar_arrive(&info_full[gi % FB_NINFO]);
@@ -324,7 +333,22 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 }
             }
         }
-      }   // warp 3: no role (it pads the control warpgroup so that setmaxnreg can hand its registers on)
+      } else if (warp == 3 && zero_flags != nullptr) {
+        // ================================================================= zero-fill of grad_source, one slice per CTA and sample
+        const long long per_sample = (long long)Hs * Ws * C * 2;                    // bytes (multiple of 128: C is a multiple of 64)
+        const long long slice = ((per_sample / 16 + gridDim.x - 1) / gridDim.x) * 16;
+        const long long lo = min(per_sample, slice * blockIdx.x), hi = min(per_sample, lo + slice);
+        const int b_first = (int)(blockIdx.x / (gxn * gyn));                        // sample of this CTA's first group
+        for (int zb = 0; zb < B; ++zb) {
+            while (zb > max(*cur_sample, b_first) + 2) __nanosleep(256);            // stay at most two samples ahead
+            char* base = reinterpret_cast<char*>(gsrc) + (long long)zb * per_sample;
+            for (long long o = lo + lane * 16; o < hi; o += 512)
+                asm volatile("st.global.v4.b32 [%0], {%1, %1, %1, %1};" ::"l"(base + o), "r"(0u) : "memory");
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(&zero_flags[zb], 1u);
+        }
+      }   // (warp 3 otherwise idle: it pads the control warpgroup so that setmaxnreg can hand its registers on)
     } else if (warp < 8) {
         // ================================================================= pixel team: the (k+1)^2 window dot products Q of every pixel
         // Extraction only: per Q stage TMEM -> thread-private staging row -> picks with dynamic shared addresses.  After the
@@ -581,9 +605,21 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         const int q = warp & 3, t = q * 32 + lane;          // block row t/32, column t%32 (as a PIXEL index for the irregular pass: 16 wide)
         const uint32_t o_base = smem_u32(smem + SM::OFF_O);
         uint32_t u = 0, oi = 0;   // oi: running index of the staging tile (alternates between the two buffers)
-        int gi = 0;
+        int gi = 0, zeroed_b = -1;
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
             const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
+            if (zero_flags != nullptr && b != zeroed_b) {      // first adds into this sample: its zero-fill must be complete
+                if (lane == 0) {
+                    unsigned int seen;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(zero_flags + b) : "memory");
+                        if (seen < gridDim.x) __nanosleep(128);
+                    } while (seen < gridDim.x);
+                }
+                __syncwarp();
+                asm volatile("fence.proxy.async;" ::: "memory");   // the zeros were written through the generic proxy, the reduce-adds go through the async one
+                zeroed_b = b;
+            }
             // ---- irregular pixels of this group (thread <-> pixel t): literal scatter, warp-cooperative
             if (!(knobs & 512)) {
                 const int px = gx0 + (t & 15), py = gy0 + (t >> 4);
@@ -699,7 +735,8 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
 
 template <int K, int CN>
 static int launch_fused(const void* src, const void* flow, const void* logits, const void* gout, void* gsrc, void* gflow,
-                        void* glogits, int B, int C, int Hs, int Ws, int H, int W, int accumulate, cudaStream_t st_) {
+                        void* glogits, int B, int C, int Hs, int Ws, int H, int W, int accumulate, void* workspace,
+                        long long workspace_bytes, cudaStream_t st_) {
     static const PFN_tmapEncodeTiled enc = tmap_encoder();
     if (enc == nullptr) return GFLA_E_NOTSUP;
     CUtensorMap tg, ts;
@@ -728,14 +765,20 @@ static int launch_fused(const void* src, const void* flow, const void* logits, c
     auto kern = k_local_attn_bwd_fused<K, CN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemFB<CN>::ALLOC);
     if (e != cudaSuccess) return static_cast<int>(e);
-    if (!accumulate) {   // the reduce-adds need a zero-filled grad_source; nothing was written before this point
-        const int z = zero_async(gsrc, (size_t)B * C * Hs * Ws * 2, st_);
+    // the reduce-adds need a zero-filled grad_source (nothing was written before this point): with a workspace of >= 4*B bytes
+    // the kernel zero-fills it itself, just ahead of its own adds (no separate pass, the zeros never travel to HBM and back);
+    // without one, a memset in front of the launch
+    unsigned int* zero_flags = nullptr;
+    if (!accumulate) {
+        const bool in_kernel = workspace != nullptr && workspace_bytes >= 4LL * B && aligned(workspace, 4) && tune_knob("GFLA_BWD_ZERO_IN_KERNEL", 1) != 0;
+        const int z = in_kernel ? zero_async(workspace, (size_t)4 * B, st_) : zero_async(gsrc, (size_t)B * C * Hs * Ws * 2, st_);
         if (z != GFLA_OK) return z;
+        if (in_kernel) zero_flags = static_cast<unsigned int*>(workspace);
     }
     const int ngroups = B * ((H + GH - 1) / GH) * ((W + GW - 1) / GW);
     kern<<<(unsigned)min(ngroups, sm_count()), FB_THREADS, SmemFB<CN>::ALLOC, st_>>>(
         tg, ts, tgs, (const __nv_bfloat16*)src, (const float*)flow, (const __nv_bfloat16*)logits, (const __nv_bfloat16*)gout,
-        (__nv_bfloat16*)gsrc, (float*)gflow, (__nv_bfloat16*)glogits, B, C, Hs, Ws, H, W, accumulate, tune_knob("GFLA_BWD_KNOBS", 0));
+        (__nv_bfloat16*)gsrc, (float*)gflow, (__nv_bfloat16*)glogits, B, C, Hs, Ws, H, W, accumulate, tune_knob("GFLA_BWD_KNOBS", 0), zero_flags);
     return launch_status();
 }
 
@@ -750,9 +793,10 @@ bool local_attn_bwd_fused_supported(int C, int k, const void* src) {
 // accumulate = 0: grad_source is zero-filled here (after the tensor maps exist, i.e. after the last point of failure
 // other than the launch itself) and all three gradients are overwritten; 1: everything is added into the caller's buffers.
 int local_attn_bwd_fused_tc(const void* src, const void* flow, const void* logits, const void* gout, void* gsrc, void* gflow,
-                            void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate, cudaStream_t st_) {
+                            void* glogits, int B, int C, int Hs, int Ws, int H, int W, int k, int accumulate, void* workspace,
+                            long long workspace_bytes, cudaStream_t st_) {
 #define GFLA_FB_CASE(K_, CN_) \
-    if (k == K_ && C == CN_) return tc::launch_fused<K_, CN_>(src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, accumulate, st_);
+    if (k == K_ && C == CN_) return tc::launch_fused<K_, CN_>(src, flow, logits, gout, gsrc, gflow, glogits, B, C, Hs, Ws, H, W, accumulate, workspace, workspace_bytes, st_);
     GFLA_FB_CASE(5, 256) GFLA_FB_CASE(5, 128) GFLA_FB_CASE(5, 64)
     GFLA_FB_CASE(3, 256) GFLA_FB_CASE(3, 128) GFLA_FB_CASE(3, 64)
 #undef GFLA_FB_CASE

@@ -247,7 +247,10 @@ def local_attn_bwd(source, flow, logits, grad_out, k, algo="auto"):
     _, _, h, w = flow.size()
     gs, gf, gl = _like_layout(source, source.shape, layout), torch.empty_like(flow), torch.empty_like(logits)
     with torch.cuda.device_of(source):
-        _lib.check(_lib.lib().gfla_local_attn_bwd(_p(source), _p(flow), _p(logits), _p(grad_out), _p(gs), _p(gf), _p(gl),
-                                                  bs, ds, hs, ws, h, w, k, _dt(source), _dt(flow), layout, 0, ALGO[algo],
-                                                  _stream(source)), "local_attn_bwd")
+        # scratch for the fused kernel's in-kernel zero-fill of grad_source (per-sample counters; the library never allocates)
+        nws = int(_lib.lib().gfla_local_attn_bwd_workspace_bytes(bs))
+        wsb = torch.empty(max(nws, 4), dtype=torch.uint8, device=source.device)
+        _lib.check(_lib.lib().gfla_local_attn_bwd_ws(_p(source), _p(flow), _p(logits), _p(grad_out), _p(gs), _p(gf), _p(gl),
+                                                     bs, ds, hs, ws, h, w, k, _dt(source), _dt(flow), layout, 0, ALGO[algo],
+                                                     _p(wsb), nws, _stream(source)), "local_attn_bwd")
     return gs, gf, gl

@@ -187,6 +187,19 @@ int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits
                         int B, int C, int Hs, int Ws, int H, int W, int k,
                         int dtype, int flow_dtype, int layout, int accumulate, int algo,
                         gfla_stream_t stream);
+/* The same backward with a caller-provided scratch buffer (DEVICE memory, >= gfla_local_attn_bwd_workspace_bytes(B) bytes,
+ * 4-byte aligned, contents irrelevant, may be reused by the next call on the same stream).  With it -- and accumulate = 0 --
+ * the fused tcgen05 backward zero-fills grad_source INSIDE the kernel, sample by sample just ahead of its own reduce-adds
+ * (per-sample completion counters live in the workspace), instead of a separate memset pass in front of it: one pass less
+ * over the 2*C*Hs*Ws*B bytes, and the zeros are still in L2 when the adds land on them.  workspace = NULL behaves exactly
+ * like gfla_local_attn_bwd.  The library itself never allocates. */
+long long gfla_local_attn_bwd_workspace_bytes(int B);
+int gfla_local_attn_bwd_ws(const void* source, const void* flow, const void* logits,
+                           const void* grad_out,
+                           void* grad_source, void* grad_flow, void* grad_logits,
+                           int B, int C, int Hs, int Ws, int H, int W, int k,
+                           int dtype, int flow_dtype, int layout, int accumulate, int algo,
+                           void* workspace, long long workspace_bytes, gfla_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ def _declared():
     text = open(os.path.join(ROOT, "include", "gfla_warp.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     decls = {}
-    for m in re.finditer(r"\b(?:int|const char\*|unsigned long long)\s+(gfla_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+    for m in re.finditer(r"\b(?:int|const char\*|unsigned long long|long long)\s+(gfla_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
         args = [a.strip() for a in m.group(2).split(",")]
         decls[m.group(1)] = 0 if args == ["void"] else len(args)
     return decls
