@@ -136,8 +136,9 @@ def cpu_reference_run(steps, warmup, flow_kind="smooth", rows=REF_ROWS):
     sample of the cfg2 workload: B=1, full C=256, k=5, a FIXED strip of `rows` rows x 256 columns, fp32
     (the reference has no bf16), the same flow family as the GPU arm.  Thread count is set explicitly
     (torchrun exports OMP_NUM_THREADS=1): the host build's atomics (`#pragma omp atomic` standing in for
-    atomicAdd) collide C*k*k-fold on grad_flow, so more threads are not always faster -- a short probe picks
-    the better of {1, all cores} and `cores` states what the timed steps used.
+    atomicAdd) collide C*k*k-fold on grad_flow, so more threads are not always faster (128 threads across two sockets
+    measured 5x SLOWER than 64 on one) -- a short probe picks the best of {1, 8, 32, half, all} cores and `cores` states what
+    the timed steps used.
     Returns the cpu_baseline dict and per-step seconds."""
     import numpy as np
     import torch
@@ -166,7 +167,7 @@ def cpu_reference_run(steps, warmup, flow_kind="smooth", rows=REF_ROWS):
     cores = 1
     if kind == "reference":
         probe = {}
-        for n in sorted({1, ncpu}):
+        for n in sorted({n for n in (1, 8, 32, ncpu // 2, ncpu) if 1 <= n <= ncpu}):
             lib.set_threads(n)
             run(8)                                       # page-in / thread-pool warm-up
             probe[n] = run(8)
@@ -179,7 +180,7 @@ def cpu_reference_run(steps, warmup, flow_kind="smooth", rows=REF_ROWS):
     mpx = rows * W / sec / 1e6
     return {"value": mpx, "unit": UNIT, "cores": cores, "host_cores": ncpu, "kind": kind,
             "sample": f"B=1 C={C} k={k} fp32, fixed strip of {rows} rows x {W} cols of the 256x256 map, {flow_kind} flow, fwd+bwd, "
-                      f"{steps} steps (+{warmup} warm-up), unfused reference pipeline; threads = best of {{1, {ncpu}}} on an 8-row probe"}, sec
+                      f"{steps} steps (+{warmup} warm-up), unfused reference pipeline; threads = best of {{1, 8, 32, {ncpu // 2}, {ncpu}}} on an 8-row probe"}, sec
 
 
 def bind_to_gpu_numa_node(torch, local_rank):

@@ -269,7 +269,7 @@ int gfla_local_attn_bwd(const void* source, const void* flow, const void* logits
                               flow_dtype, layout, accumulate, algo, nullptr, 0, stream);
 }
 
-long long gfla_local_attn_bwd_workspace_bytes(int B) { return B > 0 ? 4LL * B : 0; }
+long long gfla_local_attn_bwd_workspace_bytes(int B) { return B > 0 ? 4LL * B + 4LL * 4096 : 0; }   // counters per sample + a progress word per CTA (<= SM count)
 
 int gfla_local_attn_bwd_ws(const void* source, const void* flow, const void* logits, const void* grad_out,
                            void* grad_source, void* grad_flow, void* grad_logits, int B, int C, int Hs, int Ws, int H, int W,

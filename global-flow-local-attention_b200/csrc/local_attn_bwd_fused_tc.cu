@@ -81,7 +81,7 @@ struct SmemFB {
     static constexpr int OFF_BAR = OFF_INFO + FB_NINFO * 32;
     static constexpr int NBAR = 2 + 2 * NS + 2 * NQ + 2 * NA + 4 + 2 + FB_NINFO;
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
-    static constexpr int ALLOC = OFF_TMEM + 16 + 1024;      // OFF_TMEM + 0: TMEM base address, + 4: sample the producer is working on
+    static constexpr int ALLOC = OFF_TMEM + 16 + 1024;
     static constexpr int GS_COL0 = 256;                        // TMEM column of the first grad_source accumulator
 };
 static_assert(SmemFB<256>::ALLOC <= 232448, "shared memory budget");
@@ -144,7 +144,9 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
     uint64_t* info_full = qw_empty + 1;              // [FB_NINFO]
     FbInfo* infos = reinterpret_cast<FbInfo*>(smem + SM::OFF_INFO);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::OFF_TMEM);
-    volatile int* cur_sample = reinterpret_cast<volatile int*>(smem + SM::OFF_TMEM + 4);
+    // progress of this CTA (sample its producer is working on), read by its zero-fill warp: a word of the workspace in GLOBAL
+    // memory (a shared-memory word would do, but an unsynchronised shared word is a racecheck hazard by construction)
+    volatile unsigned int* cur_sample = zero_flags != nullptr ? zero_flags + B + blockIdx.x : nullptr;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long t_start = tc_profile_clock();
@@ -153,7 +155,6 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
     const long long hw = (long long)H * W;
 
     if (threadIdx.x == 0) {
-        *cur_sample = 0;
         mbar_init(g_full, 1);
         mbar_init(g_empty, 2);      // one commit from each MMA-issuing warp
         for (int i = 0; i < NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
@@ -195,7 +196,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
             const int ncb = (x1 - x0 + FB_BW) / FB_BW, nrows = y1 - y0 + 1, nst = ncb * nrows;
             if (lane == 0) {
-                *cur_sample = b;
+                if (cur_sample != nullptr) *cur_sample = (unsigned int)b;
                 const int wl = x1 - (x0 + FB_BW * (ncb - 1)) + 1;
                 infos[gi % FB_NINFO] = FbInfo{x0, y0, ncb, nrows, wl <= 24 ? 24 : (wl <= 28 ? 28 : 32), 0, 0, 0};
                 mbar_arrive(&info_full[gi % FB_NINFO]);
@@ -340,7 +341,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         const long long lo = min(per_sample, slice * blockIdx.x), hi = min(per_sample, lo + slice);
         const int b_first = (int)(blockIdx.x / (gxn * gyn));                        // sample of this CTA's first group
         for (int zb = 0; zb < B; ++zb) {
-            while (zb > max(*cur_sample, b_first) + 2) __nanosleep(256);            // stay at most two samples ahead
+            while (zb > max((int)*cur_sample, b_first) + 2) __nanosleep(256);       // stay at most two samples ahead
             char* base = reinterpret_cast<char*>(gsrc) + (long long)zb * per_sample;
             for (long long o = lo + lane * 16; o < hi; o += 512)
                 asm volatile("st.global.v4.b32 [%0], {%1, %1, %1, %1};" ::"l"(base + o), "r"(0u) : "memory");
@@ -765,13 +766,14 @@ static int launch_fused(const void* src, const void* flow, const void* logits, c
     auto kern = k_local_attn_bwd_fused<K, CN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemFB<CN>::ALLOC);
     if (e != cudaSuccess) return static_cast<int>(e);
-    // the reduce-adds need a zero-filled grad_source (nothing was written before this point): with a workspace of >= 4*B bytes
+    // the reduce-adds need a zero-filled grad_source (nothing was written before this point): with a workspace (gfla_local_attn_bwd_workspace_bytes)
     // the kernel zero-fills it itself, just ahead of its own adds (no separate pass, the zeros never travel to HBM and back);
     // without one, a memset in front of the launch
     unsigned int* zero_flags = nullptr;
     if (!accumulate) {
-        const bool in_kernel = workspace != nullptr && workspace_bytes >= 4LL * B && aligned(workspace, 4) && tune_knob("GFLA_BWD_ZERO_IN_KERNEL", 1) != 0;
-        const int z = in_kernel ? zero_async(workspace, (size_t)4 * B, st_) : zero_async(gsrc, (size_t)B * C * Hs * Ws * 2, st_);
+        const long long need = 4LL * B + 4LL * sm_count();     // per-sample counters + one progress word per CTA
+        const bool in_kernel = workspace != nullptr && workspace_bytes >= need && aligned(workspace, 4) && tune_knob("GFLA_BWD_ZERO_IN_KERNEL", 1) != 0;
+        const int z = in_kernel ? zero_async(workspace, (size_t)need, st_) : zero_async(gsrc, (size_t)B * C * Hs * Ws * 2, st_);
         if (z != GFLA_OK) return z;
         if (in_kernel) zero_flags = static_cast<unsigned int*>(workspace);
     }
