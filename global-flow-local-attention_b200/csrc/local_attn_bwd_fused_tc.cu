@@ -246,6 +246,8 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 }
             }
         }
+        // no groups left: release the zero-fill warp for the remaining samples (other CTAs wait for this CTA's slice of them)
+        if (lane == 0 && cur_sample != nullptr) *cur_sample = (unsigned int)B;
       } else if (warp == 1) {
         // ================================================================= MMA issuer 1: Q stages
         // Two issuing warps, one per contraction: each blocks only on its own chain's barriers, so a grad_source block

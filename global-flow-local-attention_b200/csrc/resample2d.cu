@@ -13,8 +13,14 @@
 // Layout on the machine (not the reference's):
 //   * one thread per output PIXEL (b,y,x); the 4*(ks/2)^2 weights and clamped
 //     tap offsets live in registers and are reused for every channel;
-//     consecutive lanes own consecutive x, so every per-channel access is a
-//     coalesced row segment; channel slices in grid.y for small images;
+//     a CTA owns a 32 x 4 (grad_input1: 32 x 8) pixel tile: a warp is a 128-byte
+//     row segment, and the ks rows a pixel row reads are shared with the rows
+//     above / below through L1 (one-row CTAs pulled every source row ks times
+//     over the L2 -> L1 fabric: 6.4x the tensor, profiles/r2_resample2d.md);
+//     channel slices in grid.y for small images;
+//   * grad_input1 (fp32): the CTA accumulates the scatter of its tile in a shared-memory
+//     box around the tile's footprint and flushes the box with one coalesced red.global
+//     per element -- (2*ks/2)^2 global atomics per (pixel, channel) become ~3;
 //   * grad_input2: the reference runs 3*H*W threads that each stride twice
 //     through all C channel planes; here one thread per pixel accumulates the
 //     4*(ks/2)^2 corner dot products sum_c g[c]*v[c,corner] in ONE pass and
@@ -39,6 +45,24 @@ struct RsTaps {
     A sigma;
     int flx, fly;           // floor(x + dx), floor(y + dy)
 };
+
+// CTA = 32 x TH pixel tile of one sample; blockIdx.x enumerates (sample, tile row, tile column)
+struct RsPixel { int x, y, b; bool active; };
+template <int TH>
+__device__ __forceinline__ RsPixel rs_pixel(int H, int W) {
+    const int tiles_x = (W + 31) >> 5, tiles_y = (H + TH - 1) / TH;
+    unsigned t = blockIdx.x;
+    const int tx = (int)(t % (unsigned)tiles_x); t /= (unsigned)tiles_x;
+    const int ty = (int)(t % (unsigned)tiles_y);
+    RsPixel p;
+    p.b = (int)(t / (unsigned)tiles_y);
+    p.x = tx * 32 + (int)(threadIdx.x & 31);
+    p.y = ty * TH + (int)(threadIdx.x >> 5);
+    p.active = p.x < W && p.y < H;
+    return p;
+}
+template <int TH>
+static inline long long rs_tiles(int B, int H, int W) { return (long long)B * ((H + TH - 1) / TH) * ((W + 31) >> 5); }
 
 template <typename A, int NT>
 __device__ __forceinline__ void rs_setup(RsTaps<A, NT>& t, const A* __restrict__ in2, int b, int y, int x, int H, int W,
@@ -94,10 +118,9 @@ template <typename A, int NT>
 __global__ void __launch_bounds__(128)
 k_resample2d_fwd(const A* __restrict__ in1, const A* __restrict__ in2, A* __restrict__ out, int B, int C, int Hi, int Wi,
                  int H, int W, int dil, int c_per_slice) {
-    const long long total = (long long)B * H * W;
-    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= total) return;
-    const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+    const RsPixel px = rs_pixel<4>(H, W);
+    if (!px.active) return;
+    const int x = px.x, y = px.y, b = px.b;
     RsTaps<A, NT> t;
     rs_setup<A, NT>(t, in2, b, y, x, H, W, Hi, Wi, dil, false);
     A w[NT * NT * 4];
@@ -123,20 +146,24 @@ k_resample2d_fwd(const A* __restrict__ in1, const A* __restrict__ in2, A* __rest
     }
 }
 
-// grad_input1: a scatter of 4*(ks/2)^2 weighted copies of grad_out per (pixel, channel).  When the 32 pixels of a
-// warp are a run of one image row whose taps are the same integer shift (the usual case for a smooth flow) and no
-// tap is clamped, lane L's contribution to column (x_L + shift + co) is exactly what lane L+co accumulates for its
-// own centre column: the (2*ks/2)^2 scalar atomics per element collapse to one red.global per tap ROW per lane
-// (plus the few taps that leave the warp's 32 columns) after a register-level exchange with __shfl_sync.
+// grad_input1: a scatter of 4*(ks/2)^2 weighted copies of grad_out per (pixel, channel) (:180-199).  A CTA owns a
+// 32 x 8 pixel tile.  Its taps fall into the box [min floor - (NT-1)*dil, max floor + NT*dil] of the tile's flow (clamped to
+// the image like the taps themselves); when that box fits RS_BOX_W x RS_BOX_H (any flow that does not tear the tile apart) the
+// scatter of RS_CH channels goes into shared memory and the box is flushed with ONE red.global per element, a warp per box row.
+// Otherwise (and for double) every tap is a global atomic, as in the reference.
+constexpr int RS_TH1 = 8, RS_BOX_W = 64, RS_BOX_H = 24, RS_CH = 4;
+
 template <typename A, int NT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * RS_TH1)
 k_resample2d_bwd_in1(const A* __restrict__ in2, const A* __restrict__ gout, A* __restrict__ gin1, int B, int C, int Hi,
-                     int Wi, int H, int W, int dil, int c_per_slice, int warp_rows) {
-    const long long total = (long long)B * H * W;
-    const long long pix_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = pix_raw < total;
-    const long long pix = active ? pix_raw : total - 1;   // inactive lanes stay alive for the warp shuffles
-    const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+                     int Wi, int H, int W, int dil, int c_per_slice) {
+    constexpr bool kBox = sizeof(A) == 4;
+    __shared__ float box[kBox ? RS_CH * RS_BOX_H * RS_BOX_W : 1];
+    __shared__ int ext[4][RS_TH1];
+    const RsPixel px = rs_pixel<RS_TH1>(H, W);
+    const bool active = px.active;
+    const int x = min(px.x, W - 1), y = min(px.y, H - 1), b = px.b;   // inactive lanes stay alive for the CTA barriers
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     RsTaps<A, NT> t;
     rs_setup<A, NT>(t, in2, b, y, x, H, W, Hi, Wi, dil, true);  // truncating fraction for the weights
     const A sum = rs_weight_sum<A, NT>(t);
@@ -154,49 +181,70 @@ k_resample2d_bwd_in1(const A* __restrict__ in2, const A* __restrict__ gout, A* _
     A* gi = gin1 + ((long long)b * C + c0) * ipl;
     const A* go = gout + ((long long)b * C + c0) * opl + (long long)y * W + x;
 
-    bool fast = false;
-    if (NT <= 2) {
+    bool use_box = false;
+    int x_lo = 0, y_lo = 0, bw = 0, bh = 0;
+    const int big = 1 << 28;   // far outside any image: the taps clamp to the border either way, and +- (NT*dil) cannot overflow
+    const int fx_ = max(-big, min(big, t.flx)), fy_ = max(-big, min(big, t.fly));
+    if (kBox) {
         const unsigned full = 0xffffffffu;
-        bool ok = active && warp_rows && dil == 1 && t.flx - (NT - 1) >= 0 && t.flx + NT <= Wi - 1 &&
-                  t.fly - (NT - 1) >= 0 && t.fly + NT <= Hi - 1;
-        const int shift = t.flx - x;
-        // warp-collective: every lane executes the shuffles (no short-circuit in front of them)
-        const int shift0 = __shfl_sync(full, shift, 0);
-        const int fly0 = __shfl_sync(full, t.fly, 0);
-        ok = ok && (shift == shift0) && (t.fly == fly0);
-        fast = __all_sync(full, ok);
-    }
-    if (fast) {
-        constexpr int N2 = 2 * NT;   // taps per axis: offsets -(NT-1) .. NT around (fly, flx)
-        const unsigned full = 0xffffffffu;
-        const int lane = threadIdx.x & 31;
-        double wg[N2 * N2];          // weight of (row offset ri-(NT-1), column offset ci-(NT-1))
+        // extent of floor(x + dx), floor(y + dy) over the tile
+        const int mnx = __reduce_min_sync(full, active ? fx_ : big), mxx = __reduce_max_sync(full, active ? fx_ : -big);
+        const int mny = __reduce_min_sync(full, active ? fy_ : big), mxy = __reduce_max_sync(full, active ? fy_ : -big);
+        if (lane == 0) { ext[0][warp] = mnx; ext[1][warp] = mxx; ext[2][warp] = mny; ext[3][warp] = mxy; }
+        for (int i = threadIdx.x; i < RS_CH * RS_BOX_H * RS_BOX_W; i += 32 * RS_TH1) box[i] = 0.f;
+        __syncthreads();
+        int e0 = big, e1 = -big, e2 = big, e3 = -big;
 #pragma unroll
-        for (int fy = 0; fy < NT; ++fy)
+        for (int wv = 0; wv < RS_TH1; ++wv) {
+            e0 = min(e0, ext[0][wv]); e1 = max(e1, ext[1][wv]); e2 = min(e2, ext[2][wv]); e3 = max(e3, ext[3][wv]);
+        }
+        if (e0 <= e1) {   // at least one active pixel
+            x_lo = clampi(e0 - (NT - 1) * dil, Wi - 1);
+            y_lo = clampi(e2 - (NT - 1) * dil, Hi - 1);
+            bw = clampi(e1 + NT * dil, Wi - 1) - x_lo + 1;
+            bh = clampi(e3 + NT * dil, Hi - 1) - y_lo + 1;
+            use_box = bw <= RS_BOX_W && bh <= RS_BOX_H;
+        }
+    }
+    if (use_box) {
+        int toff[NT * NT * 4];   // the clamped taps of rs_setup, as offsets into the box
+#pragma unroll
+        for (int fy = 0; fy < NT; ++fy) {
+            const int yT = clampi(fy_ - fy * dil, Hi - 1) - y_lo, yB = clampi(fy_ + (fy + 1) * dil, Hi - 1) - y_lo;
 #pragma unroll
             for (int fx = 0; fx < NT; ++fx) {
-                const double* q = wn + (fy * NT + fx) * 4;
-                wg[(NT - 1 - fy) * N2 + (NT - 1 - fx)] = q[0];   // yT, xL
-                wg[(NT - 1 - fy) * N2 + (NT + fx)] = q[1];       // yT, xR
-                wg[(NT + fy) * N2 + (NT - 1 - fx)] = q[2];       // yB, xL
-                wg[(NT + fy) * N2 + (NT + fx)] = q[3];           // yB, xR
+                const int xL = clampi(fx_ - fx * dil, Wi - 1) - x_lo, xR = clampi(fx_ + (fx + 1) * dil, Wi - 1) - x_lo;
+                int* o = toff + (fy * NT + fx) * 4;
+                o[0] = yT * RS_BOX_W + xL; o[1] = yT * RS_BOX_W + xR; o[2] = yB * RS_BOX_W + xL; o[3] = yB * RS_BOX_W + xR;
             }
-        const int centre = (t.fly - (NT - 1)) * Wi + t.flx;      // first tap row, this lane's centre column
-        for (int c = c0; c < c1; ++c, gi += ipl, go += opl) {
-            const double g = static_cast<double>(*go);
+        }
+        A* gbox = gi + (long long)y_lo * Wi + x_lo;
+        for (int c = c0; c < c1; c += RS_CH, go += RS_CH * opl, gbox += RS_CH * ipl) {
+            const int nch = min(RS_CH, c1 - c);
+            if (active) {
 #pragma unroll
-            for (int ri = 0; ri < N2; ++ri) {
-                A acc = static_cast<A>(0);
+                for (int j = 0; j < RS_CH; ++j) {
+                    if (j < nch) {
+                        const double g = static_cast<double>(go[j * opl]);
+                        float* bj = box + j * (RS_BOX_H * RS_BOX_W);
 #pragma unroll
-                for (int ci = 0; ci < N2; ++ci) {
-                    const int co = ci - (NT - 1);
-                    const A v = static_cast<A>(wg[ri * N2 + ci] * g);
-                    const A recv = __shfl_sync(full, v, (lane - co) & 31);   // what lane - co sends to column offset co = me
-                    if (lane - co >= 0 && lane - co < 32) acc += recv;
-                    if (lane + co < 0 || lane + co > 31) atomicAdd(gi + centre + ri * Wi + co, v);   // leaves the warp's span
+                        for (int q = 0; q < NT * NT * 4; ++q) atomicAdd(bj + toff[q], static_cast<float>(wn[q] * g));
+                    }
                 }
-                atomicAdd(gi + centre + ri * Wi, acc);
             }
+            __syncthreads();
+            for (int j = 0; j < nch; ++j)
+                for (int r = warp; r < bh; r += RS_TH1) {
+                    float* row = box + j * (RS_BOX_H * RS_BOX_W) + r * RS_BOX_W;
+                    for (int col = lane; col < bw; col += 32) {
+                        const float v = row[col];
+                        if (v != 0.f) {
+                            row[col] = 0.f;
+                            atomicAdd(reinterpret_cast<float*>(gbox) + j * ipl + (long long)r * Wi + col, v);
+                        }
+                    }
+                }
+            __syncthreads();
         }
         return;
     }
@@ -213,10 +261,9 @@ template <typename A, int NT>
 __global__ void __launch_bounds__(128)
 k_resample2d_bwd_in2(const A* __restrict__ in1, const A* __restrict__ in2, const A* __restrict__ gout,
                      A* __restrict__ gin2, int B, int C, int Hi, int Wi, int H, int W, int dil, int accumulate) {
-    const long long total = (long long)B * H * W;
-    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= total) return;
-    const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+    const RsPixel px = rs_pixel<4>(H, W);
+    if (!px.active) return;
+    const int x = px.x, y = px.y, b = px.b;
     RsTaps<A, NT> t;
     rs_setup<A, NT>(t, in2, b, y, x, H, W, Hi, Wi, dil, false);
     const A sum = rs_weight_sum<A, NT>(t);
@@ -273,7 +320,7 @@ static int rs_launch_fwd(const void* in1, const void* in2, void* out, int B, int
                          cudaStream_t st_) {
     const long long total = (long long)B * H * W;
     const int threads = 128, slices0 = channel_splits(total, C, threads), cps = (C + slices0 - 1) / slices0;
-    dim3 grid((unsigned)((total + threads - 1) / threads), (unsigned)((C + cps - 1) / cps));
+    dim3 grid((unsigned)rs_tiles<4>(B, H, W), (unsigned)((C + cps - 1) / cps));
     k_resample2d_fwd<A, NT><<<grid, threads, 0, st_>>>((const A*)in1, (const A*)in2, (A*)out, B, C, Hi, Wi, H, W, dil, cps);
     return launch_status();
 }
@@ -282,13 +329,13 @@ template <typename A, int NT>
 static int rs_launch_bwd(const void* in1, const void* in2, const void* gout, void* gin1, void* gin2, int B, int C, int Hi,
                          int Wi, int H, int W, int dil, int accumulate, cudaStream_t st_) {
     const long long total = (long long)B * H * W;
-    const int threads = 128, slices0 = channel_splits(total, C, threads), cps = (C + slices0 - 1) / slices0;
-    dim3 grid((unsigned)((total + threads - 1) / threads), (unsigned)((C + cps - 1) / cps));
-    k_resample2d_bwd_in1<A, NT><<<grid, threads, 0, st_>>>((const A*)in2, (const A*)gout, (A*)gin1, B, C, Hi, Wi, H, W, dil, cps,
-                                                           (W % 32 == 0) ? 1 : 0);
+    const int threads = 32 * RS_TH1, slices0 = channel_splits(total, C, threads);
+    const int cps = ((C + slices0 - 1) / slices0 + RS_CH - 1) / RS_CH * RS_CH;      // whole shared-memory channel groups per slice
+    dim3 grid((unsigned)rs_tiles<RS_TH1>(B, H, W), (unsigned)((C + cps - 1) / cps));
+    k_resample2d_bwd_in1<A, NT><<<grid, threads, 0, st_>>>((const A*)in2, (const A*)gout, (A*)gin1, B, C, Hi, Wi, H, W, dil, cps);
     int e = launch_status();
     if (e) return e;
-    k_resample2d_bwd_in2<A, NT><<<(unsigned)((total + threads - 1) / threads), threads, 0, st_>>>(
+    k_resample2d_bwd_in2<A, NT><<<(unsigned)rs_tiles<4>(B, H, W), 128, 0, st_>>>(
         (const A*)in1, (const A*)in2, (const A*)gout, (A*)gin2, B, C, Hi, Wi, H, W, dil, accumulate);
     return launch_status();
 }

@@ -532,6 +532,24 @@ def test_local_attn_bwd_tile_vs_oracle(F_, oracle_lib, shape, kind):
     np.testing.assert_allclose(host(gf), ogf, rtol=2e-2, atol=2e-2 * max(1.0, float(np.abs(ogf).max())))
 
 
+@pytest.mark.parametrize("shape", [(6, 64, 16, 16, 3), (8, 128, 32, 32, 5), (9, 64, 8, 40, 3)])
+def test_local_attn_bwd_tile_many_samples_few_groups(F_, oracle_lib, shape):
+    """More samples than a CTA ever visits (one or two groups per CTA, B > 3): every CTA still has to zero-fill its slice of ALL
+    samples of grad_source, also those it never computes on (in-kernel zero fill of the fused backward; the generator's
+    32x32 / 64x64 attention levels at batch 8 are this case)."""
+    B, C, H, W, k = shape
+    s, f, l = _tile_inputs(B, C, H, W, H, W, k, "smooth", seed=sum(shape))
+    s = s.contiguous(memory_format=torch.channels_last)
+    rng = np.random.default_rng(11)
+    g = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32)).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    for _ in range(2):     # second call: the workspace comes back dirty from the allocator
+        gs, gf, gl = F_.local_attn_bwd(s, f, l, g, k, algo="tile")
+    ogs, ogf, ogl = oracle_lib.local_attn_bwd(host(s), f.cpu().numpy(), host(l), host(g), k)
+    np.testing.assert_allclose(host(gs), ogs, rtol=0, atol=1e-2 * max(1.0, float(np.abs(ogs).max())))
+    np.testing.assert_allclose(host(gl), ogl, rtol=0, atol=1e-2)
+    np.testing.assert_allclose(host(gf), ogf, rtol=2e-2, atol=2e-2 * max(1.0, float(np.abs(ogf).max())))
+
+
 def test_local_attn_bwd_tile_irregular_taps(F_, oracle_lib):
     rng = np.random.default_rng(43)
     B, C, H, W, k = 1, 64, 24, 64, 5
@@ -677,11 +695,38 @@ def test_block_extractor_bf16_backward_fp32_accumulation(F_, oracle_lib):
     np.testing.assert_allclose(host(gf), ogf, rtol=1e-3, atol=1e-3 * max(1.0, float(np.abs(ogf).max())))
 
 
+@pytest.mark.parametrize("cfg", [(4, 1, "smooth"), (2, 1, "smooth"), (4, 2, "smooth"), (4, 1, "torn"), (6, 1, "smooth"), (4, 1, "far")])
+def test_resample2d_backward_shared_box_scatter(F_, oracle_lib, cfg):
+    """fp32 grad_input1: a CTA scatters its 32x8 pixel tile into a shared-memory box around the tile's footprint and flushes the
+    box (resample2d.cu).  Ragged tiles (H % 8, W % 32 != 0), channel groups that do not divide C, dilation 2, a flow that tears
+    some tiles apart (footprint wider than the box -> those CTAs scatter straight to global memory while their neighbours use
+    the box) and a flow that leaves the image (every tap clamped onto the border column): all against the oracle."""
+    ks, dil, kind = cfg
+    rng = np.random.default_rng(ks * 7 + dil + len(kind))
+    B, C, H, W = 2, 7, 21, 70
+    a = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    if kind == "smooth":
+        fl = np.stack([3.0 * np.sin(xx / 9.0) + 0.3 * yy, 2.5 * np.cos(yy / 5.0) - 0.2 * xx / 4], 0)[None].repeat(B, 0)
+    elif kind == "torn":       # columns 40.. of the middle tile jump 45 pixels to the left: its footprint is > 64 wide
+        fl = np.stack([np.where(xx >= 40, -45.0, 1.5) + 0.3 * rng.random((H, W)), 0.7 * rng.random((H, W))], 0)[None].repeat(B, 0)
+    else:
+        fl = np.stack([np.full((H, W), 500.0), -300.0 + rng.random((H, W))], 0)[None].repeat(B, 0)
+    fl = fl + 0.05 * rng.standard_normal(fl.shape)
+    in2 = np.ascontiguousarray(np.concatenate([fl, np.full((B, 1, H, W), 2.0)], 1).astype(np.float32))
+    g = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    g1, g2 = F_.resample2d_bwd(cu(a), cu(in2), cu(g), ks, dil)
+    o1, o2 = oracle_lib.resample2d_bwd(a, in2, g, ks, dil)
+    np.testing.assert_allclose(host(g1), o1, rtol=1e-5, atol=1e-5 * max(1.0, float(np.abs(o1).max())))
+    np.testing.assert_allclose(host(g2), o2, rtol=1e-4, atol=1e-4 * max(1.0, float(np.abs(o2).max())))
+    out = F_.resample2d_fwd(cu(a), cu(in2), ks, dil)
+    np.testing.assert_allclose(host(out), oracle_lib.resample2d_fwd(a, in2, ks, dil), rtol=1e-6, atol=1e-6)
+
+
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("cfg", [(2, 5.0, "uniform"), (4, 2.0, "uniform"), (4, 2.0, "mixed"), (2, 5.0, "border")])
-def test_resample2d_backward_warp_merged_scatter(F_, oracle_lib, dt, cfg):
-    """grad_input1 with W % 32 == 0: warps whose 32 pixels share one integer tap shift merge their scatter through
-    shuffles (one red per tap row); the others (and clamped taps) keep the scalar path.  Both against the oracle."""
+def test_resample2d_backward_uniform_mixed_border_flows(F_, oracle_lib, dt, cfg):
+    """grad_input1 on flows with one integer tap shift per row, a shift that changes mid-row, and taps clamped at the border"""
     ks, sigma, kind = cfg
     rng = np.random.default_rng(ks + len(kind))
     B, C, H, W = 2, 5, 9, 64

@@ -6,8 +6,8 @@ nvidia-smi topo -m > gpurun_out/r2_topo.txt 2>&1
 for n in 1 2 4 8; do
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500+n)) bench.py --gpus $n --workload cfg4 --arms fused,literal --steps 10 --warmup 3 > gpurun_out/r2_cfg4_n$n.json 2> gpurun_out/r2_cfg4_n$n.err; echo "cfg4 n=$n rc=$?"
 done
-for n in 1 8; do
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600+n)) bench.py --gpus $n --workload cfg5 --arms fused,literal --steps 5 --warmup 3 > gpurun_out/r2_cfg5_n$n.json 2> gpurun_out/r2_cfg5_n$n.err; echo "cfg5 n=$n rc=$?"
+for n in 8; do
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600+n)) bench.py --gpus $n --workload cfg5 --arms fused,literal --steps 3 --warmup 3 > gpurun_out/r2_cfg5_n$n.json 2> gpurun_out/r2_cfg5_n$n.err; echo "cfg5 n=$n rc=$?"
 done
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29700 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r2_cfg2_n8.json 2> gpurun_out/r2_cfg2_n8.err; echo "cfg2 n=8 rc=$?"
 for f in gpurun_out/r2_cfg4_n*.json gpurun_out/r2_cfg5_n*.json; do echo "== $f"; python -c "
