@@ -223,6 +223,7 @@ def extras(torch, F_, dev, args, peak, peak_kind):
       iid_flow        the same cfg2 step with iid U(-8,8) flow (adversarial for the tiling)
       cfg3            BASELINE config 3: resample2d fwd+bwd, B=32 C=128 512x512 fp32, kernel_size 2 (module default) and 4
                       (what training uses), each with its own HBM roofline (1036 / 1560 algorithmic B per pixel)
+      f4_resample_cosine   the fused resample2d -> cosine op vs the unfused modules, fwd+bwd
       reference_cuda  the reference's own CUDA kernels recompiled for sm_100a (oracle/_ref/libgfla_ref_cuda.so), running the
                       unfused ExtractorAttn tail in fp32 on 2 samples of the cfg2 shape -- the same-box GPU baseline"""
     out = {}
@@ -263,6 +264,38 @@ def extras(torch, F_, dev, args, peak, peak_kind):
         del x, go, flow
     except Exception as exc:
         out["cfg3"] = {"error": repr(exc)[:200]}
+    torch.cuda.empty_cache()
+    try:
+        # f4: PerceptualCorrectness' resample -> cosine step at the VGG relu3_1 / relu2_1 shapes of a 256x256 batch of 16
+        # (external_function.py:275-279): ONE fused kernel each way vs Resample2d + F.cosine_similarity through autograd;
+        # gradient to the flow only, like the loss
+        import gfla_b200
+        f4 = {}
+        for name, (Bf, Cf, Hf) in (("relu3_1", (16, 256, 64)), ("relu2_1", (16, 128, 128))):
+            gen = torch.Generator(device="cpu").manual_seed(Hf)
+            xs = torch.randn(Bf, Cf, Hf, Hf, generator=gen).to(dev)
+            tg = torch.randn(Bf, Cf, Hf, Hf, generator=gen).to(dev)
+            coarse = torch.rand(Bf, 2, Hf // 8, Hf // 8, generator=gen) * 8 - 4
+            fl = torch.nn.functional.interpolate(coarse, size=(Hf, Hf)).to(dev).requires_grad_()     # nearest, like the loss (:254)
+            fused_m, plain_m = gfla_b200.Resample2dCosine(4, 1, sigma=2), gfla_b200.Resample2d(4, 1, sigma=2)
+            go = torch.randn(Bf, Hf, Hf, device=dev)
+
+            def fused():
+                fl.grad = None
+                fused_m(xs, fl, tg).backward(go)
+
+            def unfused():
+                fl.grad = None
+                torch.nn.functional.cosine_similarity(plain_m(xs, fl), tg, dim=1, eps=1e-8).backward(go)
+            t_f, t_u = _time(torch, fused, 3, 10), _time(torch, unfused, 3, 10)
+            alg = Bf * Hf * Hf * (2 * 2 * Cf * 4 + 60)            # source + target read once each way, per-pixel planes
+            f4[name] = {"shape": [Bf, Cf, Hf, Hf], "fused_ms": t_f, "unfused_ms": t_u, "speedup": t_u / t_f,
+                        "roofline_frac": alg / (t_f * 1e-3) / 1e9 / peak}
+            del xs, tg, fl, go
+        f4["workload"] = "resample2d(ks 4, sigma 2) -> cosine_similarity fwd+bwd (grad to the flow), fp32, blocky (nearest-upsampled) flow"
+        out["f4_resample_cosine"] = f4
+    except Exception as exc:
+        out["f4_resample_cosine"] = {"error": repr(exc)[:200]}
     torch.cuda.empty_cache()
     try:
         import oracle.ref_cuda as rc
@@ -433,43 +466,46 @@ def main():
 
         # The batch is processed in 4-sample chunks alternating between 2 streams, so the H2D of chunk i+1 overlaps the
         # kernels and the D2H of chunk i (PCIe is full duplex; every byte is still copied inside the timed region, through
-        # the public autograd API, once per step).  Host buffers are pinned on the GPU's own NUMA node (see above).
+        # the public autograd API, once per step).  The two streams are joined to the timing stream once in front of the
+        # first step and once behind the last one -- consecutive steps pipeline like consecutive chunks (a chunk always
+        # returns to the stream that handled the same host slices in the previous step, so host buffers are reused in order).
+        # Host buffers are pinned on the GPU's own NUMA node (see above).
         chunks = [(b0, min(B, b0 + 4)) for b0 in range(0, B, 4)]
         side = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        assert len(chunks) % len(side) == 0 or len(chunks) == 1
 
-        def e2e_step():
+        def e2e_steps_run(n):
             main = torch.cuda.current_stream(dev)
             for st in side:
                 st.wait_stream(main)
-            for ci, (b0, b1) in enumerate(chunks):
-                with torch.cuda.stream(side[ci % 2]):
-                    s = hs[b0:b1].to(dev, non_blocking=True).requires_grad_()
-                    f = hf[b0:b1].to(dev, non_blocking=True).requires_grad_()
-                    l = hl[b0:b1].to(dev, non_blocking=True).requires_grad_()
-                    g = hg[b0:b1].to(dev, non_blocking=True)
-                    out = gfla_b200.local_attention(s, f, l, k)          # the call a user makes
-                    out.backward(g)
-                    ho[b0:b1].copy_(out.detach(), non_blocking=True)
-                    hgs[b0:b1].copy_(s.grad, non_blocking=True)
-                    hgf[b0:b1].copy_(f.grad, non_blocking=True)
-                    hgl[b0:b1].copy_(l.grad, non_blocking=True)
+            for _ in range(n):
+                for ci, (b0, b1) in enumerate(chunks):
+                    with torch.cuda.stream(side[ci % 2]):
+                        s = hs[b0:b1].to(dev, non_blocking=True).requires_grad_()
+                        f = hf[b0:b1].to(dev, non_blocking=True).requires_grad_()
+                        l = hl[b0:b1].to(dev, non_blocking=True).requires_grad_()
+                        g = hg[b0:b1].to(dev, non_blocking=True)
+                        out = gfla_b200.local_attention(s, f, l, k)          # the call a user makes
+                        out.backward(g)
+                        ho[b0:b1].copy_(out.detach(), non_blocking=True)
+                        hgs[b0:b1].copy_(s.grad, non_blocking=True)
+                        hgf[b0:b1].copy_(f.grad, non_blocking=True)
+                        hgl[b0:b1].copy_(l.grad, non_blocking=True)
             for st in side:
                 main.wait_stream(st)
 
         e2e_steps = steps
-        for _ in range(2):
-            e2e_step()
+        e2e_steps_run(2)
         barrier()
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(e2e_steps):
-            e2e_step()
+        e2e_steps_run(e2e_steps)
         b_.record()
         barrier()
         e2e_ms = reduce_max_time(a.elapsed_time(b_), dev) / e2e_steps
         e2e = {"value": world * B * H * W / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps, "numa_node": numa_node,
-               "chunks": len(chunks), "streams": len(side)}
+               "chunks": len(chunks), "streams": len(side), "pipelined_across_steps": True}
     if rank == 0:
         sampler.stop()
 

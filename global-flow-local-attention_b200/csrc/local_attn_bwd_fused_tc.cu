@@ -229,7 +229,8 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 mbar_arrive_expect_tx(g_full, SM::G_BYTES);
 #pragma unroll
                 for (int cg = 0; cg < CN / 64; ++cg)
-                    tma_load_4d(smem + SM::OFF_G + cg * SM::G_CG, &tmap_g, g_full, cg * 64, gx0, gy0, b);
+                    if (knobs & 8192) tma_load_4d_hint(smem + SM::OFF_G + cg * SM::G_CG, &tmap_g, g_full, cg * 64, gx0, gy0, b, l2_policy_evict_first());
+                    else tma_load_4d(smem + SM::OFF_G + cg * SM::G_CG, &tmap_g, g_full, cg * 64, gx0, gy0, b);
                 if (has_next) {
 #pragma unroll
                     for (int cg = 0; cg < CN / 64; ++cg) tma_prefetch_4d(&tmap_g, cg * 64, ngx0, ngy0, nb);
@@ -342,11 +343,17 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         const long long slice = ((per_sample / 16 + gridDim.x - 1) / gridDim.x) * 16;
         const long long lo = min(per_sample, slice * blockIdx.x), hi = min(per_sample, lo + slice);
         const int b_first = (int)(blockIdx.x / (gxn * gyn));                        // sample of this CTA's first group
+        const int ahead = (knobs & 2048) ? 1 : 2;
+        const uint64_t keep = l2_policy_evict_last();
         for (int zb = 0; zb < B; ++zb) {
-            while (zb > max((int)*cur_sample, b_first) + 2) __nanosleep(256);       // stay at most two samples ahead
+            while (zb > max((int)*cur_sample, b_first) + ahead) __nanosleep(256);   // stay at most `ahead` samples ahead
             char* base = reinterpret_cast<char*>(gsrc) + (long long)zb * per_sample;
-            for (long long o = lo + lane * 16; o < hi; o += 512)
-                asm volatile("st.global.v4.b32 [%0], {%1, %1, %1, %1};" ::"l"(base + o), "r"(0u) : "memory");
+            if (knobs & 4096) {
+                for (long long o = lo + lane * 16; o < hi; o += 512) stg128_zero_hint(base + o, keep);
+            } else {
+                for (long long o = lo + lane * 16; o < hi; o += 512)
+                    asm volatile("st.global.v4.b32 [%0], {%1, %1, %1, %1};" ::"l"(base + o), "r"(0u) : "memory");
+            }
             __threadfence();
             __syncwarp();
             if (lane == 0) atomicAdd(&zero_flags[zb], 1u);
@@ -719,8 +726,12 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                             fence_proxy_async_smem();
                             fb_named_bar_sync(2, 128);        // tile complete
                             if (warp == 12 && elect_one()) {
-                                tma_reduce_add_4d(rmap, o_base + (oi & 1) * SM::O_BUF, hf * HN + cg * 64, inf.x0 + cb * FB_BW,
-                                                  inf.y0 + rb * FB_GROWS, b);
+                                if (knobs & 16384)
+                                    tma_reduce_add_4d_hint(rmap, o_base + (oi & 1) * SM::O_BUF, hf * HN + cg * 64, inf.x0 + cb * FB_BW,
+                                                           inf.y0 + rb * FB_GROWS, b, l2_policy_evict_last());
+                                else
+                                    tma_reduce_add_4d(rmap, o_base + (oi & 1) * SM::O_BUF, hf * HN + cg * 64, inf.x0 + cb * FB_BW,
+                                                      inf.y0 + rb * FB_GROWS, b);
                                 bulk_commit();
                                 bulk_wait_read<1>();          // the OTHER buffer's reduce has finished reading smem
                             }

@@ -13,14 +13,15 @@
 // Layout on the machine (not the reference's):
 //   * one thread per output PIXEL (b,y,x); the 4*(ks/2)^2 weights and clamped
 //     tap offsets live in registers and are reused for every channel;
-//     a CTA owns a 32 x 4 (grad_input1: 32 x 8) pixel tile: a warp is a 128-byte
+//     a CTA owns a 32 x 4 pixel tile: a warp is a 128-byte
 //     row segment, and the ks rows a pixel row reads are shared with the rows
 //     above / below through L1 (one-row CTAs pulled every source row ks times
 //     over the L2 -> L1 fabric: 6.4x the tensor, profiles/r2_resample2d.md);
 //     channel slices in grid.y for small images;
-//   * grad_input1 (fp32): the CTA accumulates the scatter of its tile in a shared-memory
-//     box around the tile's footprint and flushes the box with one coalesced red.global
-//     per element -- (2*ks/2)^2 global atomics per (pixel, channel) become ~3;
+//   * grad_input1: warps whose taps are one integer shift of their pixel run merge the scatter through shuffles.
+//     (Measured and dropped, profiles/r2_resample2d.md: accumulating the CTA's scatter in a shared-memory box and
+//     flushing the box -- fp32 shared-memory atomics are ATOMS.CAST.SPIN loops, 2.6 tries and 7 wavefronts per
+//     add on a stretching flow, no faster than the L2's native fp32 RED.)
 //   * grad_input2: the reference runs 3*H*W threads that each stride twice
 //     through all C channel planes; here one thread per pixel accumulates the
 //     4*(ks/2)^2 corner dot products sum_c g[c]*v[c,corner] in ONE pass and
@@ -146,24 +147,18 @@ k_resample2d_fwd(const A* __restrict__ in1, const A* __restrict__ in2, A* __rest
     }
 }
 
-// grad_input1: a scatter of 4*(ks/2)^2 weighted copies of grad_out per (pixel, channel) (:180-199).  A CTA owns a
-// 32 x 8 pixel tile.  Its taps fall into the box [min floor - (NT-1)*dil, max floor + NT*dil] of the tile's flow (clamped to
-// the image like the taps themselves); when that box fits RS_BOX_W x RS_BOX_H (any flow that does not tear the tile apart) the
-// scatter of RS_CH channels goes into shared memory and the box is flushed with ONE red.global per element, a warp per box row.
-// Otherwise (and for double) every tap is a global atomic, as in the reference.
-constexpr int RS_TH1 = 8, RS_BOX_W = 64, RS_BOX_H = 24, RS_CH = 4;
-
+// grad_input1: a scatter of 4*(ks/2)^2 weighted copies of grad_out per (pixel, channel).  A warp is a 32-pixel run of one
+// image row (rs_pixel).  When its taps are the same integer shift (the usual case for a smooth flow) and no
+// tap is clamped, lane L's contribution to column (x_L + shift + co) is exactly what lane L+co accumulates for its
+// own centre column: the (2*ks/2)^2 scalar atomics per element collapse to one red.global per tap ROW per lane
+// (plus the few taps that leave the warp's 32 columns) after a register-level exchange with __shfl_sync.
 template <typename A, int NT>
-__global__ void __launch_bounds__(32 * RS_TH1)
+__global__ void __launch_bounds__(128)
 k_resample2d_bwd_in1(const A* __restrict__ in2, const A* __restrict__ gout, A* __restrict__ gin1, int B, int C, int Hi,
                      int Wi, int H, int W, int dil, int c_per_slice) {
-    constexpr bool kBox = sizeof(A) == 4;
-    __shared__ float box[kBox ? RS_CH * RS_BOX_H * RS_BOX_W : 1];
-    __shared__ int ext[4][RS_TH1];
-    const RsPixel px = rs_pixel<RS_TH1>(H, W);
+    const RsPixel px = rs_pixel<4>(H, W);
     const bool active = px.active;
-    const int x = min(px.x, W - 1), y = min(px.y, H - 1), b = px.b;   // inactive lanes stay alive for the CTA barriers
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = min(px.x, W - 1), y = min(px.y, H - 1), b = px.b;   // inactive lanes stay alive for the warp shuffles
     RsTaps<A, NT> t;
     rs_setup<A, NT>(t, in2, b, y, x, H, W, Hi, Wi, dil, true);  // truncating fraction for the weights
     const A sum = rs_weight_sum<A, NT>(t);
@@ -181,70 +176,49 @@ k_resample2d_bwd_in1(const A* __restrict__ in2, const A* __restrict__ gout, A* _
     A* gi = gin1 + ((long long)b * C + c0) * ipl;
     const A* go = gout + ((long long)b * C + c0) * opl + (long long)y * W + x;
 
-    bool use_box = false;
-    int x_lo = 0, y_lo = 0, bw = 0, bh = 0;
-    const int big = 1 << 28;   // far outside any image: the taps clamp to the border either way, and +- (NT*dil) cannot overflow
-    const int fx_ = max(-big, min(big, t.flx)), fy_ = max(-big, min(big, t.fly));
-    if (kBox) {
+    bool fast = false;
+    if (NT <= 2) {
         const unsigned full = 0xffffffffu;
-        // extent of floor(x + dx), floor(y + dy) over the tile
-        const int mnx = __reduce_min_sync(full, active ? fx_ : big), mxx = __reduce_max_sync(full, active ? fx_ : -big);
-        const int mny = __reduce_min_sync(full, active ? fy_ : big), mxy = __reduce_max_sync(full, active ? fy_ : -big);
-        if (lane == 0) { ext[0][warp] = mnx; ext[1][warp] = mxx; ext[2][warp] = mny; ext[3][warp] = mxy; }
-        for (int i = threadIdx.x; i < RS_CH * RS_BOX_H * RS_BOX_W; i += 32 * RS_TH1) box[i] = 0.f;
-        __syncthreads();
-        int e0 = big, e1 = -big, e2 = big, e3 = -big;
-#pragma unroll
-        for (int wv = 0; wv < RS_TH1; ++wv) {
-            e0 = min(e0, ext[0][wv]); e1 = max(e1, ext[1][wv]); e2 = min(e2, ext[2][wv]); e3 = max(e3, ext[3][wv]);
-        }
-        if (e0 <= e1) {   // at least one active pixel
-            x_lo = clampi(e0 - (NT - 1) * dil, Wi - 1);
-            y_lo = clampi(e2 - (NT - 1) * dil, Hi - 1);
-            bw = clampi(e1 + NT * dil, Wi - 1) - x_lo + 1;
-            bh = clampi(e3 + NT * dil, Hi - 1) - y_lo + 1;
-            use_box = bw <= RS_BOX_W && bh <= RS_BOX_H;
-        }
+        bool ok = active && dil == 1 && t.flx - (NT - 1) >= 0 && t.flx + NT <= Wi - 1 &&
+                  t.fly - (NT - 1) >= 0 && t.fly + NT <= Hi - 1;
+        const int shift = t.flx - x;
+        // warp-collective: every lane executes the shuffles (no short-circuit in front of them)
+        const int shift0 = __shfl_sync(full, shift, 0);
+        const int fly0 = __shfl_sync(full, t.fly, 0);
+        ok = ok && (shift == shift0) && (t.fly == fly0);
+        fast = __all_sync(full, ok);
     }
-    if (use_box) {
-        int toff[NT * NT * 4];   // the clamped taps of rs_setup, as offsets into the box
+    if (fast) {
+        constexpr int N2 = 2 * NT;   // taps per axis: offsets -(NT-1) .. NT around (fly, flx)
+        const unsigned full = 0xffffffffu;
+        const int lane = threadIdx.x & 31;
+        double wg[N2 * N2];          // weight of (row offset ri-(NT-1), column offset ci-(NT-1))
 #pragma unroll
-        for (int fy = 0; fy < NT; ++fy) {
-            const int yT = clampi(fy_ - fy * dil, Hi - 1) - y_lo, yB = clampi(fy_ + (fy + 1) * dil, Hi - 1) - y_lo;
+        for (int fy = 0; fy < NT; ++fy)
 #pragma unroll
             for (int fx = 0; fx < NT; ++fx) {
-                const int xL = clampi(fx_ - fx * dil, Wi - 1) - x_lo, xR = clampi(fx_ + (fx + 1) * dil, Wi - 1) - x_lo;
-                int* o = toff + (fy * NT + fx) * 4;
-                o[0] = yT * RS_BOX_W + xL; o[1] = yT * RS_BOX_W + xR; o[2] = yB * RS_BOX_W + xL; o[3] = yB * RS_BOX_W + xR;
+                const double* q = wn + (fy * NT + fx) * 4;
+                wg[(NT - 1 - fy) * N2 + (NT - 1 - fx)] = q[0];   // yT, xL
+                wg[(NT - 1 - fy) * N2 + (NT + fx)] = q[1];       // yT, xR
+                wg[(NT + fy) * N2 + (NT - 1 - fx)] = q[2];       // yB, xL
+                wg[(NT + fy) * N2 + (NT + fx)] = q[3];           // yB, xR
             }
-        }
-        A* gbox = gi + (long long)y_lo * Wi + x_lo;
-        for (int c = c0; c < c1; c += RS_CH, go += RS_CH * opl, gbox += RS_CH * ipl) {
-            const int nch = min(RS_CH, c1 - c);
-            if (active) {
+        const int centre = (t.fly - (NT - 1)) * Wi + t.flx;      // first tap row, this lane's centre column
+        for (int c = c0; c < c1; ++c, gi += ipl, go += opl) {
+            const double g = static_cast<double>(*go);
 #pragma unroll
-                for (int j = 0; j < RS_CH; ++j) {
-                    if (j < nch) {
-                        const double g = static_cast<double>(go[j * opl]);
-                        float* bj = box + j * (RS_BOX_H * RS_BOX_W);
+            for (int ri = 0; ri < N2; ++ri) {
+                A acc = static_cast<A>(0);
 #pragma unroll
-                        for (int q = 0; q < NT * NT * 4; ++q) atomicAdd(bj + toff[q], static_cast<float>(wn[q] * g));
-                    }
+                for (int ci = 0; ci < N2; ++ci) {
+                    const int co = ci - (NT - 1);
+                    const A v = static_cast<A>(wg[ri * N2 + ci] * g);
+                    const A recv = __shfl_sync(full, v, (lane - co) & 31);   // what lane - co sends to column offset co = me
+                    if (lane - co >= 0 && lane - co < 32) acc += recv;
+                    if (lane + co < 0 || lane + co > 31) atomicAdd(gi + centre + ri * Wi + co, v);   // leaves the warp's span
                 }
+                atomicAdd(gi + centre + ri * Wi, acc);
             }
-            __syncthreads();
-            for (int j = 0; j < nch; ++j)
-                for (int r = warp; r < bh; r += RS_TH1) {
-                    float* row = box + j * (RS_BOX_H * RS_BOX_W) + r * RS_BOX_W;
-                    for (int col = lane; col < bw; col += 32) {
-                        const float v = row[col];
-                        if (v != 0.f) {
-                            row[col] = 0.f;
-                            atomicAdd(reinterpret_cast<float*>(gbox) + j * ipl + (long long)r * Wi + col, v);
-                        }
-                    }
-                }
-            __syncthreads();
         }
         return;
     }
@@ -257,29 +231,9 @@ k_resample2d_bwd_in1(const A* __restrict__ in2, const A* __restrict__ gout, A* _
     }
 }
 
+// d/d(dx, dy, sigma) of one pixel from its corner dot products D[q] = sum_c g[c] * in1[c, tap q]
 template <typename A, int NT>
-__global__ void __launch_bounds__(128)
-k_resample2d_bwd_in2(const A* __restrict__ in1, const A* __restrict__ in2, const A* __restrict__ gout,
-                     A* __restrict__ gin2, int B, int C, int Hi, int Wi, int H, int W, int dil, int accumulate) {
-    const RsPixel px = rs_pixel<4>(H, W);
-    if (!px.active) return;
-    const int x = px.x, y = px.y, b = px.b;
-    RsTaps<A, NT> t;
-    rs_setup<A, NT>(t, in2, b, y, x, H, W, Hi, Wi, dil, false);
-    const A sum = rs_weight_sum<A, NT>(t);
-    // corner dot products over the channels: D[q] = sum_c g[c] * in1[c, tap q]
-    A D[NT * NT * 4];
-#pragma unroll
-    for (int q = 0; q < NT * NT * 4; ++q) D[q] = static_cast<A>(0);
-    const long long ipl = (long long)Hi * Wi, opl = (long long)H * W;
-    const A* s = in1 + (long long)b * C * ipl;
-    const A* go = gout + (long long)b * C * opl + (long long)y * W + x;
-#pragma unroll 4
-    for (int c = 0; c < C; ++c, s += ipl, go += opl) {
-        const A g = *go;
-#pragma unroll
-        for (int q = 0; q < NT * NT * 4; ++q) D[q] += g * s[t.off[q]];
-    }
+__device__ __forceinline__ void rs_in2_store(const RsTaps<A, NT>& t, A sum, const A* D, A* gp, long long opl, int accumulate) {
     // combine (per pixel, in double): reference :271-296 (grad1, sumgrad), :304-326 (grad2), :328
     const double sg = static_cast<double>(t.sigma);
     const bool s0 = (t.sigma == static_cast<A>(0));
@@ -307,12 +261,142 @@ k_resample2d_bwd_in2(const A* __restrict__ in1, const A* __restrict__ in2, const
     const double inv1 = (sum == static_cast<A>(0)) ? 1e8 : 1.0 / S;
     const double S2 = static_cast<double>(sum * sum);
     const double inv2 = (sum * sum == static_cast<A>(0)) ? 1e8 : 1.0 / S2;
-    A* gp = gin2 + (long long)b * 3 * opl + (long long)y * W + x;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const A v = static_cast<A>(g1[c] * inv1 - (sgrad[c] * wd) * inv2);
         gp[c * opl] = accumulate ? gp[c * opl] + v : v;
     }
+}
+
+template <typename A, int NT>
+__global__ void __launch_bounds__(128)
+k_resample2d_bwd_in2(const A* __restrict__ in1, const A* __restrict__ in2, const A* __restrict__ gout,
+                     A* __restrict__ gin2, int B, int C, int Hi, int Wi, int H, int W, int dil, int accumulate) {
+    const RsPixel px = rs_pixel<4>(H, W);
+    if (!px.active) return;
+    const int x = px.x, y = px.y, b = px.b;
+    RsTaps<A, NT> t;
+    rs_setup<A, NT>(t, in2, b, y, x, H, W, Hi, Wi, dil, false);
+    const A sum = rs_weight_sum<A, NT>(t);
+    // corner dot products over the channels: D[q] = sum_c g[c] * in1[c, tap q]
+    A D[NT * NT * 4];
+#pragma unroll
+    for (int q = 0; q < NT * NT * 4; ++q) D[q] = static_cast<A>(0);
+    const long long ipl = (long long)Hi * Wi, opl = (long long)H * W;
+    const A* s = in1 + (long long)b * C * ipl;
+    const A* go = gout + (long long)b * C * opl + (long long)y * W + x;
+#pragma unroll 4
+    for (int c = 0; c < C; ++c, s += ipl, go += opl) {
+        const A g = *go;
+#pragma unroll
+        for (int q = 0; q < NT * NT * 4; ++q) D[q] += g * s[t.off[q]];
+    }
+    rs_in2_store<A, NT>(t, sum, D, gin2 + (long long)b * 3 * opl + (long long)y * W + x, opl, accumulate);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// resample2d -> cosine similarity with a target feature map, fused.
+// PerceptualCorrectness.calculate_loss (external_function.py:275-279) warps the source VGG features with Resample2d, writes
+// them out, and reads them back once for F.cosine_similarity(input_sample, target_all) over the channel axis.  Here a pixel's
+// thread warps one channel at a time in registers and folds it straight into the three sums the cosine needs; the warped
+// tensor never exists.  cos = sum_c (v_c / max(|v|, eps)) * (t_c / max(|t|, eps))  (ATen's cosine_similarity: each norm clamped).
+// stats[b, 0..2, y, x] = (v.t, |v|, |t|) are kept for the backward.
+template <typename A, int NT>
+__global__ void __launch_bounds__(128)
+k_resample2d_cos_fwd(const A* __restrict__ in1, const A* __restrict__ in2, const A* __restrict__ target, A* __restrict__ cos_out,
+                     A* __restrict__ stats, int B, int C, int Hi, int Wi, int H, int W, int dil, A eps) {
+    const RsPixel px = rs_pixel<4>(H, W);
+    if (!px.active) return;
+    const int x = px.x, y = px.y, b = px.b;
+    RsTaps<A, NT> t;
+    rs_setup<A, NT>(t, in2, b, y, x, H, W, Hi, Wi, dil, false);
+    A w[NT * NT * 4];
+#pragma unroll
+    for (int fy = 0; fy < NT; ++fy)
+#pragma unroll
+        for (int fx = 0; fx < NT; ++fx) {
+            A* q = w + (fy * NT + fx) * 4;
+            q[0] = t.yT_P[fy] * t.xL_P[fx]; q[1] = t.yT_P[fy] * t.xR_P[fx];
+            q[2] = t.yB_P[fy] * t.xL_P[fx]; q[3] = t.yB_P[fy] * t.xR_P[fx];
+        }
+    const A sum = rs_weight_sum<A, NT>(t);
+    const long long ipl = (long long)Hi * Wi, opl = (long long)H * W, pix = (long long)y * W + x;
+    const A* s = in1 + (long long)b * C * ipl;
+    const A* tg = target + (long long)b * C * opl + pix;
+    A dot = static_cast<A>(0), vv = static_cast<A>(0), tt = static_cast<A>(0);
+#pragma unroll 4
+    for (int c = 0; c < C; ++c, s += ipl, tg += opl) {
+        A val = static_cast<A>(0);
+#pragma unroll
+        for (int q = 0; q < NT * NT * 4; ++q) val += w[q] * s[t.off[q]];
+        const A v = static_cast<A>(safe_div<A>(val, sum));        // exactly k_resample2d_fwd's output element
+        const A tc = *tg;
+        dot += v * tc; vv += v * v; tt += tc * tc;
+    }
+    const A nv = sqrt(vv), nt = sqrt(tt);
+    cos_out[(long long)b * opl + pix] = dot / (max(nv, eps) * max(nt, eps));
+    A* st = stats + (long long)b * 3 * opl + pix;
+    st[0] = dot; st[opl] = nv; st[2 * opl] = nt;
+}
+
+// Backward of the fused op for one pixel, one pass over the channels: the warped value v_c is rebuilt from the taps that are in
+// registers anyway, g_c = dcos/dv_c * grad_cos follows from the saved sums, and the corner dot products of grad_input2 accumulate
+// g_c * tap -- so the flow gradient (the one PerceptualCorrectness trains through) costs one read of the source and the
+// target and writes 3 floats per pixel.  grad_val (optional) receives g_c for the grad_input1 scatter (k_resample2d_bwd_in1 runs on
+// it afterwards; VGG features of data carry no gradient in the reference's use), grad_target (optional) dcos/dt_c * grad_cos.
+template <typename A, int NT>
+__global__ void __launch_bounds__(128)
+k_resample2d_cos_bwd(const A* __restrict__ in1, const A* __restrict__ in2, const A* __restrict__ target, const A* __restrict__ stats,
+                     const A* __restrict__ gcos, A* __restrict__ gin2, A* __restrict__ gval, A* __restrict__ gtarget, int B, int C,
+                     int Hi, int Wi, int H, int W, int dil, A eps, int accumulate) {
+    const RsPixel px = rs_pixel<4>(H, W);
+    if (!px.active) return;
+    const int x = px.x, y = px.y, b = px.b;
+    RsTaps<A, NT> t;
+    rs_setup<A, NT>(t, in2, b, y, x, H, W, Hi, Wi, dil, false);
+    A w[NT * NT * 4], D[NT * NT * 4];
+#pragma unroll
+    for (int fy = 0; fy < NT; ++fy)
+#pragma unroll
+        for (int fx = 0; fx < NT; ++fx) {
+            A* q = w + (fy * NT + fx) * 4;
+            q[0] = t.yT_P[fy] * t.xL_P[fx]; q[1] = t.yT_P[fy] * t.xR_P[fx];
+            q[2] = t.yB_P[fy] * t.xL_P[fx]; q[3] = t.yB_P[fy] * t.xR_P[fx];
+        }
+#pragma unroll
+    for (int q = 0; q < NT * NT * 4; ++q) D[q] = static_cast<A>(0);
+    const A sum = rs_weight_sum<A, NT>(t);
+    const long long ipl = (long long)Hi * Wi, opl = (long long)H * W, pix = (long long)y * W + x;
+    const A* st = stats + (long long)b * 3 * opl + pix;
+    const A dot = st[0], nv = st[opl], nt = st[2 * opl];
+    const A a = max(nv, eps), bb = max(nt, eps), g = gcos[(long long)b * opl + pix];
+    // cos = dot / (a * bb);  da/dv_c = v_c / |v| above the clamp, 0 below it
+    const A k1 = g / (a * bb);
+    const A k2v = nv > eps ? g * dot / (a * a * bb * nv) : static_cast<A>(0);
+    const A k2t = nt > eps ? g * dot / (a * bb * bb * nt) : static_cast<A>(0);
+    const A* s = in1 + (long long)b * C * ipl;
+    const long long o0 = (long long)b * C * opl + pix;
+    const A* tg = target + o0;
+    A* gv = gval != nullptr ? gval + o0 : nullptr;
+    A* gt = gtarget != nullptr ? gtarget + o0 : nullptr;
+#pragma unroll 2
+    for (int c = 0; c < C; ++c, s += ipl, tg += opl) {
+        A tap[NT * NT * 4];
+        A val = static_cast<A>(0);
+#pragma unroll
+        for (int q = 0; q < NT * NT * 4; ++q) { tap[q] = s[t.off[q]]; val += w[q] * tap[q]; }
+        const A v = static_cast<A>(safe_div<A>(val, sum));
+        const A tc = *tg;
+        const A gc = k1 * tc - k2v * v;
+#pragma unroll
+        for (int q = 0; q < NT * NT * 4; ++q) D[q] += gc * tap[q];
+        if (gv != nullptr) gv[(long long)c * opl] = gc;
+        if (gt != nullptr) {
+            const A d = k1 * v - k2t * tc;
+            gt[(long long)c * opl] = accumulate ? gt[(long long)c * opl] + d : d;
+        }
+    }
+    rs_in2_store<A, NT>(t, sum, D, gin2 + (long long)b * 3 * opl + pix, opl, accumulate);
 }
 
 template <typename A, int NT>
@@ -329,14 +413,37 @@ template <typename A, int NT>
 static int rs_launch_bwd(const void* in1, const void* in2, const void* gout, void* gin1, void* gin2, int B, int C, int Hi,
                          int Wi, int H, int W, int dil, int accumulate, cudaStream_t st_) {
     const long long total = (long long)B * H * W;
-    const int threads = 32 * RS_TH1, slices0 = channel_splits(total, C, threads);
-    const int cps = ((C + slices0 - 1) / slices0 + RS_CH - 1) / RS_CH * RS_CH;      // whole shared-memory channel groups per slice
-    dim3 grid((unsigned)rs_tiles<RS_TH1>(B, H, W), (unsigned)((C + cps - 1) / cps));
+    const int threads = 128, slices0 = channel_splits(total, C, threads), cps = (C + slices0 - 1) / slices0;
+    dim3 grid((unsigned)rs_tiles<4>(B, H, W), (unsigned)((C + cps - 1) / cps));
     k_resample2d_bwd_in1<A, NT><<<grid, threads, 0, st_>>>((const A*)in2, (const A*)gout, (A*)gin1, B, C, Hi, Wi, H, W, dil, cps);
     int e = launch_status();
     if (e) return e;
     k_resample2d_bwd_in2<A, NT><<<(unsigned)rs_tiles<4>(B, H, W), 128, 0, st_>>>(
         (const A*)in1, (const A*)in2, (const A*)gout, (A*)gin2, B, C, Hi, Wi, H, W, dil, accumulate);
+    return launch_status();
+}
+
+template <typename A, int NT>
+static int rs_launch_cos_fwd(const void* in1, const void* in2, const void* target, void* cos_out, void* stats, int B, int C, int Hi,
+                             int Wi, int H, int W, int dil, double eps, cudaStream_t st_) {
+    k_resample2d_cos_fwd<A, NT><<<(unsigned)rs_tiles<4>(B, H, W), 128, 0, st_>>>((const A*)in1, (const A*)in2, (const A*)target, (A*)cos_out,
+                                                                                 (A*)stats, B, C, Hi, Wi, H, W, dil, static_cast<A>(eps));
+    return launch_status();
+}
+
+template <typename A, int NT>
+static int rs_launch_cos_bwd(const void* in1, const void* in2, const void* target, const void* stats, const void* gcos, void* gin1,
+                             void* gin2, void* gval, void* gtarget, int B, int C, int Hi, int Wi, int H, int W, int dil, double eps,
+                             int accumulate, cudaStream_t st_) {
+    k_resample2d_cos_bwd<A, NT><<<(unsigned)rs_tiles<4>(B, H, W), 128, 0, st_>>>(
+        (const A*)in1, (const A*)in2, (const A*)target, (const A*)stats, (const A*)gcos, (A*)gin2, (A*)gval, (A*)gtarget, B, C, Hi, Wi, H,
+        W, dil, static_cast<A>(eps), accumulate);
+    int e = launch_status();
+    if (e || gin1 == nullptr) return e;
+    const long long total = (long long)B * H * W;
+    const int threads = 128, slices0 = channel_splits(total, C, threads), cps = (C + slices0 - 1) / slices0;
+    dim3 grid((unsigned)rs_tiles<4>(B, H, W), (unsigned)((C + cps - 1) / cps));
+    k_resample2d_bwd_in1<A, NT><<<grid, threads, 0, st_>>>((const A*)in2, (const A*)gval, (A*)gin1, B, C, Hi, Wi, H, W, dil, cps);
     return launch_status();
 }
 
@@ -364,6 +471,26 @@ int resample2d_bwd(const void* in1, const void* in2, const void* gout, void* gin
     }
     if (dtype == GFLA_F32) { GFLA_RS_DISPATCH(float, rs_launch_bwd, in1, in2, gout, gin1, gin2, B, C, Hi, Wi, H, W, dil, accumulate, st_) }
     if (dtype == GFLA_F64) { GFLA_RS_DISPATCH(double, rs_launch_bwd, in1, in2, gout, gin1, gin2, B, C, Hi, Wi, H, W, dil, accumulate, st_) }
+    return GFLA_E_DTYPE;
+}
+
+int resample2d_cos_fwd(const void* in1, const void* in2, const void* target, void* cos_out, void* stats, int B, int C, int Hi, int Wi,
+                       int H, int W, int ks, int dil, double eps, int dtype, cudaStream_t st_) {
+    if (dtype == GFLA_F32) { GFLA_RS_DISPATCH(float, rs_launch_cos_fwd, in1, in2, target, cos_out, stats, B, C, Hi, Wi, H, W, dil, eps, st_) }
+    if (dtype == GFLA_F64) { GFLA_RS_DISPATCH(double, rs_launch_cos_fwd, in1, in2, target, cos_out, stats, B, C, Hi, Wi, H, W, dil, eps, st_) }
+    return GFLA_E_DTYPE;
+}
+
+// grad_in1 != nullptr needs grad_val (a [B,C,H,W] scratch tensor of the caller); accumulate = 0 zero-fills grad_in1 first
+int resample2d_cos_bwd(const void* in1, const void* in2, const void* target, const void* stats, const void* gcos, void* gin1, void* gin2,
+                       void* gval, void* gtarget, int B, int C, int Hi, int Wi, int H, int W, int ks, int dil, double eps, int dtype,
+                       int accumulate, cudaStream_t st_) {
+    if (gin1 != nullptr && !accumulate) {
+        const int e = zero_async(gin1, (size_t)B * C * Hi * Wi * elem_size(dtype), st_);
+        if (e != GFLA_OK) return e;
+    }
+    if (dtype == GFLA_F32) { GFLA_RS_DISPATCH(float, rs_launch_cos_bwd, in1, in2, target, stats, gcos, gin1, gin2, gval, gtarget, B, C, Hi, Wi, H, W, dil, eps, accumulate, st_) }
+    if (dtype == GFLA_F64) { GFLA_RS_DISPATCH(double, rs_launch_cos_bwd, in1, in2, target, stats, gcos, gin1, gin2, gval, gtarget, B, C, Hi, Wi, H, W, dil, eps, accumulate, st_) }
     return GFLA_E_DTYPE;
 }
 

@@ -150,6 +150,45 @@ def resample2d_bwd(input1, input2, grad_out, kernel_size, dilation, grad_input1=
     return grad_input1, grad_input2
 
 
+def resample2d_cosine_fwd(input1, input2, target, kernel_size: int, dilation: int, eps: float = 1e-8):
+    """cos[b,y,x] = cosine_similarity(resample2d(input1, input2)[b,:,y,x], target[b,:,y,x]) without the warped tensor
+    (external_function.py:275-279).  -> (cos [B,H,W], stats [B,3,H,W] for the backward)"""
+    assert input1.is_contiguous() and input2.is_contiguous() and target.is_contiguous()
+    _need_cuda(input1, input2, target)
+    _, d, hi, wi = input1.size()
+    b, three, h, w = input2.size()
+    assert three == 3, "input2 must be [B,3,H,W] = (dx, dy, sigma) (resample2d.py:51-52)"
+    assert tuple(target.shape) == (b, d, h, w), "target must be [B,C,H,W] on the flow's grid"
+    if input2.dtype != input1.dtype or target.dtype != input1.dtype:
+        raise TypeError("resample2d_cosine: input1, input2 and target must share a dtype (float32 or float64)")
+    cos = input1.new_empty((b, h, w))
+    stats = input1.new_empty((b, 3, h, w))
+    with torch.cuda.device_of(input1):
+        _lib.check(_lib.lib().gfla_resample2d_cosine_fwd(_p(input1), _p(input2), _p(target), _p(cos), _p(stats), b, d, hi, wi, h, w,
+                                                         kernel_size, dilation, float(eps), _dt(input1), _stream(input1)),
+                   "resample2d_cosine_fwd")
+    return cos, stats
+
+
+def resample2d_cosine_bwd(input1, input2, target, stats, grad_cos, kernel_size, dilation, eps=1e-8, need_input1=False,
+                          need_target=False):
+    """-> (grad_input1 | None, grad_input2, grad_target | None)"""
+    grad_cos = grad_cos.contiguous()
+    _need_cuda(input1, input2, target, stats, grad_cos)
+    _, d, hi, wi = input1.size()
+    b, _, h, w = input2.size()
+    grad_in2 = torch.empty_like(input2)
+    grad_in1 = torch.empty_like(input1) if need_input1 else None
+    grad_val = torch.empty_like(target) if need_input1 else None
+    grad_target = torch.empty_like(target) if need_target else None
+    with torch.cuda.device_of(input1):
+        _lib.check(_lib.lib().gfla_resample2d_cosine_bwd(
+            _p(input1), _p(input2), _p(target), _p(stats), _p(grad_cos), _p(grad_in1) if need_input1 else None, _p(grad_in2),
+            _p(grad_val) if need_input1 else None, _p(grad_target) if need_target else None, b, d, hi, wi, h, w, kernel_size, dilation,
+            float(eps), _dt(input1), 0, _stream(input1)), "resample2d_cosine_bwd")
+    return grad_in1, grad_in2, grad_target
+
+
 # --------------------------------------------------------------------------- fused local attention
 ALGO = {"auto": 0, "gather": 1, "tile": 2}
 

@@ -1,4 +1,7 @@
-"""Flow-regularisation loss of the reference, without the warping ops.
+"""Losses of the reference that sit on the warping ops: the flow regularisation WITHOUT the ops (row f3) and the sampling
+correctness loss on the fused resample -> cosine op (row f4, at the end of this file).
+
+Flow-regularisation loss of the reference, without the warping ops.
 
 Reference: model/networks/external_function.py:12-77 (``MultiAffineRegularizationLoss``,
 ``AffineRegularizationLoss``).  Same constructors, same call signatures, same values -- SURVEY.md section 8 row f3.
@@ -20,6 +23,8 @@ reduction, all differentiable by autograd.  Nothing here needs the CUDA library,
 class it also runs on CPU tensors (tests/test_losses.py checks it there against the literal composition
 evaluated with the oracle's block_extractor / local_attn_reshape).
 """
+import math
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -79,3 +84,70 @@ class MultiAffineRegularizationLoss(nn.Module):
         for i in range(len(flow_fields)):
             loss += self.method_dic[self.layers[i]](flow_fields[i])
         return loss
+
+
+class PerceptualCorrectness(nn.Module):
+    """Drop-in for external_function.py:222-284 (the "sampling correctness" loss), SURVEY.md section 8 row f4.
+
+    Same call signature and value.  ``calculate_loss`` differs in ONE step: the reference warps ``source_vgg`` with
+    ``Resample2d(4, 1, sigma=2)``, writes the warped features, and reads them back for ``F.cosine_similarity`` against the
+    target features (:275-279); here that pair is the fused op ``Resample2dCosine`` -- one kernel forward, one backward, no
+    warped tensor, and in the backward no gradient work for the VGG features (they are functions of data).  The N x N
+    correlation (:262-271) stays a cuBLAS ``bmm``.
+
+    ``vgg``: the feature extractor (a module returning ``{'relu1_1': ..., ...}``).  ``None`` builds the reference's own ``VGG19``
+    (needs ``compat.install(reference_root=...)`` and torchvision's pretrained weights), which is what the reference's
+    constructor does unconditionally.  ``use_bilinear_sampling=True`` keeps the reference's ``grid_sample`` branch (:286-301).
+    """
+
+    def __init__(self, layer=['rel1_1', 'relu2_1', 'relu3_1', 'relu4_1'], vgg=None):
+        super(PerceptualCorrectness, self).__init__()
+        if vgg is None:
+            from model.networks.external_function import VGG19      # the reference's, through compat.install()
+            vgg = VGG19()
+        self.add_module('vgg', vgg)
+        self.layer = layer
+        self.eps = 1e-8
+        from .resample2d import Resample2dCosine
+        self.resample_cosine = Resample2dCosine(4, 1, sigma=2, eps=1e-8)
+
+    def __call__(self, target, source, flow_list, used_layers, mask=None, use_bilinear_sampling=False):
+        used_layers = sorted(used_layers, reverse=True)
+        self.target_vgg, self.source_vgg = self.vgg(target), self.vgg(source)
+        loss = 0
+        for i in range(len(flow_list)):
+            loss += self.calculate_loss(flow_list[i], self.layer[used_layers[i]], mask, use_bilinear_sampling)
+        return loss
+
+    def calculate_loss(self, flow, layer, mask=None, use_bilinear_sampling=False):
+        tgt, src = self.target_vgg[layer], self.source_vgg[layer]
+        b, c, h, w = tgt.shape
+        n = h * w
+        flow = F.interpolate(flow, [h, w])
+        # the best similarity any source position offers each target position (:259-271): N x N correlation of unit vectors
+        t_flat = tgt.reshape(b, c, n)
+        s_unit = src.reshape(b, c, n).transpose(1, 2)
+        s_unit = s_unit / (s_unit.norm(dim=2, keepdim=True) + self.eps)
+        t_unit = t_flat / (t_flat.norm(dim=1, keepdim=True) + self.eps)
+        best = torch.bmm(s_unit, t_unit).amax(dim=1)                                   # [b, N]
+        # the similarity the flow actually achieves (:273-279)
+        if use_bilinear_sampling:
+            achieved = F.cosine_similarity(self.bilinear_warp(src, flow), t_flat)
+        else:
+            achieved = self.resample_cosine(src, flow, tgt).reshape(b, n)              # fused: no warped feature tensor
+        loss_map = torch.exp(-achieved / (best + self.eps))
+        floor = math.exp(-1.0)                                                         # value of a perfect sample
+        if mask is None:
+            return loss_map.mean() - floor
+        m = F.interpolate(mask, size=(h, w)).reshape(-1, n)
+        return (m * (loss_map - floor)).sum() / (m.sum() + self.eps)
+
+    def bilinear_warp(self, source, flow):
+        """the ``grid_sample`` alternative of the reference (:309-320): pixel offsets -> offsets on the [-1, 1] sampling grid"""
+        b, c, h, w = source.shape
+        ys, xs = torch.meshgrid(torch.linspace(-1.0, 1.0, h, device=source.device), torch.linspace(-1.0, 1.0, w, device=source.device),
+                                indexing="ij")
+        base = torch.stack((xs, ys), dim=-1).unsqueeze(0)                              # [1, h, w, (x, y)]
+        step = torch.tensor([2.0 / w, 2.0 / h], device=source.device).view(1, 1, 1, 2)
+        grid = (base + flow.permute(0, 2, 3, 1).float() * step).type_as(source)
+        return F.grid_sample(source, grid).view(b, c, -1)

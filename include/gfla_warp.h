@@ -153,6 +153,34 @@ int gfla_resample2d_bwd(const void* in1, const void* in2, const void* grad_out,
                         int dtype, int accumulate, gfla_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
+ * resample2d -> cosine similarity, fused  
+ *   replaces, in PerceptualCorrectness.calculate_loss
+ *   (model/networks/external_function.py:275-279),
+ *       input_sample      = Resample2d(4, 1, sigma=2)(source_vgg, flow)   # resample2d_cuda.forward
+ *       correction_sample = F.cosine_similarity(input_sample, target_all) # over the channel axis
+ *   and their backward (resample2d_cuda.backward + ATen) by one kernel each
+ *   way; the warped feature tensor [B,C,H,W] is never written.
+ *   in1 = source features [B,C,Hi,Wi]; in2 [B,3,H,W] as for resample2d;
+ *   target [B,C,H,W]; cos_out [B,H,W];
+ *   cos = sum_c (v_c / max(|v|,eps)) * (t_c / max(|t|,eps))   (ATen, eps = 1e-8 in the reference call);
+ *   stats [B,3,H,W] = (v.t, |v|, |t|), written by the forward and read by the backward.
+ *   Backward: grad_cos [B,H,W] -> grad_in2 [B,3,H,W] (always);
+ *   grad_target [B,C,H,W] optional (NULL = not wanted);
+ *   grad_in1 [B,C,Hi,Wi] optional -- it needs grad_val, a caller-provided
+ *   [B,C,H,W] scratch tensor that receives d/d(warped) before the scatter.
+ *   accumulate applies to grad_in1 / grad_in2 / grad_target.  F32 or F64.
+ * ------------------------------------------------------------------------ */
+int gfla_resample2d_cosine_fwd(const void* in1, const void* in2, const void* target,
+                               void* cos_out, void* stats,
+                               int B, int C, int Hi, int Wi, int H, int W, int ks, int dilation,
+                               double eps, int dtype, gfla_stream_t stream);
+int gfla_resample2d_cosine_bwd(const void* in1, const void* in2, const void* target,
+                               const void* stats, const void* grad_cos,
+                               void* grad_in1, void* grad_in2, void* grad_val, void* grad_target,
+                               int B, int C, int Hi, int Wi, int H, int W, int ks, int dilation,
+                               double eps, int dtype, int accumulate, gfla_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
  * fused local attention = the tail of ExtractorAttn.forward
  *   (base_function.py:804-810 with softmax=True, generator.py:112):
  *     out = avg_pool2d( LocalAttnReshape(Softmax_dim1(logits)) *

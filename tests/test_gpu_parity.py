@@ -696,11 +696,10 @@ def test_block_extractor_bf16_backward_fp32_accumulation(F_, oracle_lib):
 
 
 @pytest.mark.parametrize("cfg", [(4, 1, "smooth"), (2, 1, "smooth"), (4, 2, "smooth"), (4, 1, "torn"), (6, 1, "smooth"), (4, 1, "far")])
-def test_resample2d_backward_shared_box_scatter(F_, oracle_lib, cfg):
-    """fp32 grad_input1: a CTA scatters its 32x8 pixel tile into a shared-memory box around the tile's footprint and flushes the
-    box (resample2d.cu).  Ragged tiles (H % 8, W % 32 != 0), channel groups that do not divide C, dilation 2, a flow that tears
-    some tiles apart (footprint wider than the box -> those CTAs scatter straight to global memory while their neighbours use
-    the box) and a flow that leaves the image (every tap clamped onto the border column): all against the oracle."""
+def test_resample2d_ragged_tiles_and_torn_flows(F_, oracle_lib, cfg):
+    """resample2d on 32x4 pixel tiles (resample2d.cu): ragged tiles (H % 4, W % 32 != 0), an odd channel count, dilation 2, a flow
+    that tears a tile apart (columns 40.. jump 45 pixels), and a flow that leaves the image (every tap clamped onto the border
+    column, i.e. maximal atomic contention in grad_input1): forward and both gradients against the oracle."""
     ks, dil, kind = cfg
     rng = np.random.default_rng(ks * 7 + dil + len(kind))
     B, C, H, W = 2, 7, 21, 70
