@@ -791,9 +791,24 @@ static int launch_fused(const void* src, const void* flow, const void* logits, c
         if (in_kernel) zero_flags = static_cast<unsigned int*>(workspace);
     }
     const int ngroups = B * ((H + GH - 1) / GH) * ((W + GW - 1) / GW);
-    kern<<<(unsigned)min(ngroups, sm_count()), FB_THREADS, SmemFB<CN>::ALLOC, st_>>>(
-        tg, ts, tgs, (const __nv_bfloat16*)src, (const float*)flow, (const __nv_bfloat16*)logits, (const __nv_bfloat16*)gout,
-        (__nv_bfloat16*)gsrc, (float*)gflow, (__nv_bfloat16*)glogits, B, C, Hs, Ws, H, W, accumulate, tune_knob("GFLA_BWD_KNOBS", 0), zero_flags);
+    // With the in-kernel zero fill the CTAs depend on each other (a CTA's first add into a sample waits for every CTA's slice of
+    // that sample's zeros): the grid must be co-resident, which only a COOPERATIVE launch guarantees -- a plain launch that shares the
+    // GPU with another grid (a second stream's backward, an overlapping NCCL all-reduce under DDP) may start with part of its CTAs and
+    // leave the rest waiting for SMs held by a grid in the same position.  One CTA per SM fits by construction (grid <= SM count).
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)min(ngroups, sm_count()));
+    cfg.blockDim = dim3(FB_THREADS);
+    cfg.dynamicSmemBytes = SmemFB<CN>::ALLOC;
+    cfg.stream = st_;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = zero_flags != nullptr ? 1 : 0;
+    e = cudaLaunchKernelEx(&cfg, kern, tg, ts, tgs, (const __nv_bfloat16*)src, (const float*)flow, (const __nv_bfloat16*)logits,
+                           (const __nv_bfloat16*)gout, (__nv_bfloat16*)gsrc, (float*)gflow, (__nv_bfloat16*)glogits, B, C, Hs, Ws, H, W,
+                           accumulate, (int)tune_knob("GFLA_BWD_KNOBS", 0), zero_flags);
+    if (e != cudaSuccess) { cudaGetLastError(); return static_cast<int>(e); }
     return launch_status();
 }
 

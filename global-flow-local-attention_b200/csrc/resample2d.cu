@@ -50,7 +50,7 @@ struct RsTaps {
 // CTA = 32 x TH pixel tile of one sample; blockIdx.x enumerates (sample, tile row, tile column)
 struct RsPixel { int x, y, b; bool active; };
 template <int TH>
-__device__ __forceinline__ RsPixel rs_pixel(int H, int W) {
+__device__ __forceinline__ RsPixel rs_pixel(int H, int W, int row = -1) {
     const int tiles_x = (W + 31) >> 5, tiles_y = (H + TH - 1) / TH;
     unsigned t = blockIdx.x;
     const int tx = (int)(t % (unsigned)tiles_x); t /= (unsigned)tiles_x;
@@ -58,7 +58,7 @@ __device__ __forceinline__ RsPixel rs_pixel(int H, int W) {
     RsPixel p;
     p.b = (int)(t / (unsigned)tiles_y);
     p.x = tx * 32 + (int)(threadIdx.x & 31);
-    p.y = ty * TH + (int)(threadIdx.x >> 5);
+    p.y = ty * TH + (row >= 0 ? row : (int)(threadIdx.x >> 5));
     p.active = p.x < W && p.y < H;
     return p;
 }
@@ -301,13 +301,19 @@ k_resample2d_bwd_in2(const A* __restrict__ in1, const A* __restrict__ in2, const
 // thread warps one channel at a time in registers and folds it straight into the three sums the cosine needs; the warped
 // tensor never exists.  cos = sum_c (v_c / max(|v|, eps)) * (t_c / max(|t|, eps))  (ATen's cosine_similarity: each norm clamped).
 // stats[b, 0..2, y, x] = (v.t, |v|, |t|) are kept for the backward.
-template <typename A, int NT>
+// TS > 1: the 4 warps of a CTA are TS channel slices of ONE 32-pixel row segment (feature maps of a loss are small: a thread per
+// pixel alone leaves the SMs with a handful of warps each, walking C channels one after the other); the partial sums meet in shared memory.
+template <typename A, int NT, int TS>
 __global__ void __launch_bounds__(128)
 k_resample2d_cos_fwd(const A* __restrict__ in1, const A* __restrict__ in2, const A* __restrict__ target, A* __restrict__ cos_out,
                      A* __restrict__ stats, int B, int C, int Hi, int Wi, int H, int W, int dil, A eps) {
-    const RsPixel px = rs_pixel<4>(H, W);
-    if (!px.active) return;
-    const int x = px.x, y = px.y, b = px.b;
+    constexpr int TH = 4 / TS;                                   // pixel rows per CTA
+    __shared__ A part[TS > 1 ? 3 * TS * 32 * TH : 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slice = TS > 1 ? warp % TS : 0, row = TS > 1 ? warp / TS : warp;
+    const RsPixel px = rs_pixel<TH>(H, W, row);
+    if (TS == 1 && !px.active) return;
+    const int x = min(px.x, W - 1), y = min(px.y, H - 1), b = px.b;
     RsTaps<A, NT> t;
     rs_setup<A, NT>(t, in2, b, y, x, H, W, Hi, Wi, dil, false);
     A w[NT * NT * 4];
@@ -321,17 +327,30 @@ k_resample2d_cos_fwd(const A* __restrict__ in1, const A* __restrict__ in2, const
         }
     const A sum = rs_weight_sum<A, NT>(t);
     const long long ipl = (long long)Hi * Wi, opl = (long long)H * W, pix = (long long)y * W + x;
-    const A* s = in1 + (long long)b * C * ipl;
-    const A* tg = target + (long long)b * C * opl + pix;
+    const int cs = (C + TS - 1) / TS, c0 = slice * cs, c1 = min(C, c0 + cs);
+    const A* s = in1 + ((long long)b * C + c0) * ipl;
+    const A* tg = target + ((long long)b * C + c0) * opl + pix;
     A dot = static_cast<A>(0), vv = static_cast<A>(0), tt = static_cast<A>(0);
 #pragma unroll 4
-    for (int c = 0; c < C; ++c, s += ipl, tg += opl) {
+    for (int c = c0; c < c1; ++c, s += ipl, tg += opl) {
         A val = static_cast<A>(0);
 #pragma unroll
         for (int q = 0; q < NT * NT * 4; ++q) val += w[q] * s[t.off[q]];
         const A v = static_cast<A>(safe_div<A>(val, sum));        // exactly k_resample2d_fwd's output element
         const A tc = *tg;
         dot += v * tc; vv += v * v; tt += tc * tc;
+    }
+    if (TS > 1) {
+        A* mine = part + ((row * TS + slice) * 3) * 32 + lane;
+        mine[0] = dot; mine[32] = vv; mine[64] = tt;
+        __syncthreads();
+        if (slice != 0 || !px.active) return;
+        dot = vv = tt = static_cast<A>(0);
+#pragma unroll
+        for (int sl = 0; sl < TS; ++sl) {                         // fixed order: deterministic
+            const A* o = part + ((row * TS + sl) * 3) * 32 + lane;
+            dot += o[0]; vv += o[32]; tt += o[64];
+        }
     }
     const A nv = sqrt(vv), nt = sqrt(tt);
     cos_out[(long long)b * opl + pix] = dot / (max(nv, eps) * max(nt, eps));
@@ -344,17 +363,21 @@ k_resample2d_cos_fwd(const A* __restrict__ in1, const A* __restrict__ in2, const
 // g_c * tap -- so the flow gradient (the one PerceptualCorrectness trains through) costs one read of the source and the
 // target and writes 3 floats per pixel.  grad_val (optional) receives g_c for the grad_input1 scatter (k_resample2d_bwd_in1 runs on
 // it afterwards; VGG features of data carry no gradient in the reference's use), grad_target (optional) dcos/dt_c * grad_cos.
-template <typename A, int NT>
+template <typename A, int NT, int TS>
 __global__ void __launch_bounds__(128)
 k_resample2d_cos_bwd(const A* __restrict__ in1, const A* __restrict__ in2, const A* __restrict__ target, const A* __restrict__ stats,
                      const A* __restrict__ gcos, A* __restrict__ gin2, A* __restrict__ gval, A* __restrict__ gtarget, int B, int C,
                      int Hi, int Wi, int H, int W, int dil, A eps, int accumulate) {
-    const RsPixel px = rs_pixel<4>(H, W);
-    if (!px.active) return;
-    const int x = px.x, y = px.y, b = px.b;
+    constexpr int TH = 4 / TS, NQ = NT * NT * 4;
+    __shared__ A part[TS > 1 ? NQ * TS * 32 * TH : 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slice = TS > 1 ? warp % TS : 0, row = TS > 1 ? warp / TS : warp;
+    const RsPixel px = rs_pixel<TH>(H, W, row);
+    if (TS == 1 && !px.active) return;
+    const int x = min(px.x, W - 1), y = min(px.y, H - 1), b = px.b;
     RsTaps<A, NT> t;
     rs_setup<A, NT>(t, in2, b, y, x, H, W, Hi, Wi, dil, false);
-    A w[NT * NT * 4], D[NT * NT * 4];
+    A w[NQ], D[NQ];
 #pragma unroll
     for (int fy = 0; fy < NT; ++fy)
 #pragma unroll
@@ -364,7 +387,7 @@ k_resample2d_cos_bwd(const A* __restrict__ in1, const A* __restrict__ in2, const
             q[2] = t.yB_P[fy] * t.xL_P[fx]; q[3] = t.yB_P[fy] * t.xR_P[fx];
         }
 #pragma unroll
-    for (int q = 0; q < NT * NT * 4; ++q) D[q] = static_cast<A>(0);
+    for (int q = 0; q < NQ; ++q) D[q] = static_cast<A>(0);
     const A sum = rs_weight_sum<A, NT>(t);
     const long long ipl = (long long)Hi * Wi, opl = (long long)H * W, pix = (long long)y * W + x;
     const A* st = stats + (long long)b * 3 * opl + pix;
@@ -374,26 +397,43 @@ k_resample2d_cos_bwd(const A* __restrict__ in1, const A* __restrict__ in2, const
     const A k1 = g / (a * bb);
     const A k2v = nv > eps ? g * dot / (a * a * bb * nv) : static_cast<A>(0);
     const A k2t = nt > eps ? g * dot / (a * bb * bb * nt) : static_cast<A>(0);
-    const A* s = in1 + (long long)b * C * ipl;
-    const long long o0 = (long long)b * C * opl + pix;
+    const int cs = (C + TS - 1) / TS, c0 = slice * cs, c1 = min(C, c0 + cs);
+    const A* s = in1 + ((long long)b * C + c0) * ipl;
+    const long long o0 = ((long long)b * C + c0) * opl + pix;
     const A* tg = target + o0;
-    A* gv = gval != nullptr ? gval + o0 : nullptr;
-    A* gt = gtarget != nullptr ? gtarget + o0 : nullptr;
+    const bool live = px.active;                                  // inactive lanes only keep the CTA barrier company
+    A* gv = gval != nullptr && live ? gval + o0 : nullptr;
+    A* gt = gtarget != nullptr && live ? gtarget + o0 : nullptr;
 #pragma unroll 2
-    for (int c = 0; c < C; ++c, s += ipl, tg += opl) {
-        A tap[NT * NT * 4];
+    for (int c = c0; c < c1; ++c, s += ipl, tg += opl) {
+        A tap[NQ];
         A val = static_cast<A>(0);
 #pragma unroll
-        for (int q = 0; q < NT * NT * 4; ++q) { tap[q] = s[t.off[q]]; val += w[q] * tap[q]; }
+        for (int q = 0; q < NQ; ++q) { tap[q] = s[t.off[q]]; val += w[q] * tap[q]; }
         const A v = static_cast<A>(safe_div<A>(val, sum));
         const A tc = *tg;
         const A gc = k1 * tc - k2v * v;
 #pragma unroll
-        for (int q = 0; q < NT * NT * 4; ++q) D[q] += gc * tap[q];
-        if (gv != nullptr) gv[(long long)c * opl] = gc;
+        for (int q = 0; q < NQ; ++q) D[q] += gc * tap[q];
+        if (gv != nullptr) gv[(long long)(c - c0) * opl] = gc;
         if (gt != nullptr) {
             const A d = k1 * v - k2t * tc;
-            gt[(long long)c * opl] = accumulate ? gt[(long long)c * opl] + d : d;
+            gt[(long long)(c - c0) * opl] = accumulate ? gt[(long long)(c - c0) * opl] + d : d;
+        }
+    }
+    if (TS > 1) {
+        A* mine = part + ((row * TS + slice) * NQ) * 32 + lane;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) mine[q * 32] = D[q];
+        __syncthreads();
+        if (slice != 0 || !live) return;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) D[q] = static_cast<A>(0);
+#pragma unroll
+        for (int sl = 0; sl < TS; ++sl) {
+            const A* o = part + ((row * TS + sl) * NQ) * 32 + lane;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) D[q] += o[q * 32];
         }
     }
     rs_in2_store<A, NT>(t, sum, D, gin2 + (long long)b * 3 * opl + pix, opl, accumulate);
@@ -423,11 +463,22 @@ static int rs_launch_bwd(const void* in1, const void* in2, const void* gout, voi
     return launch_status();
 }
 
+// channel slices per pixel: 4 when the map is too small to fill the machine with one thread per pixel (and C is worth splitting)
+static inline int rs_cos_slices(int B, int C, int H, int W) {
+    return (C >= 32 && (long long)B * H * W < (long long)sm_count() * 2048 * 2) ? 4 : 1;
+}
+
 template <typename A, int NT>
 static int rs_launch_cos_fwd(const void* in1, const void* in2, const void* target, void* cos_out, void* stats, int B, int C, int Hi,
                              int Wi, int H, int W, int dil, double eps, cudaStream_t st_) {
-    k_resample2d_cos_fwd<A, NT><<<(unsigned)rs_tiles<4>(B, H, W), 128, 0, st_>>>((const A*)in1, (const A*)in2, (const A*)target, (A*)cos_out,
-                                                                                 (A*)stats, B, C, Hi, Wi, H, W, dil, static_cast<A>(eps));
+    bool sliced = false;
+    if constexpr (NT <= 2) sliced = rs_cos_slices(B, C, H, W) == 4;      // (larger windows: the partial sums would not fit static shared memory)
+    if constexpr (NT <= 2) if (sliced)
+        k_resample2d_cos_fwd<A, NT, 4><<<(unsigned)rs_tiles<1>(B, H, W), 128, 0, st_>>>((const A*)in1, (const A*)in2, (const A*)target, (A*)cos_out,
+                                                                                        (A*)stats, B, C, Hi, Wi, H, W, dil, static_cast<A>(eps));
+    if (!sliced)
+        k_resample2d_cos_fwd<A, NT, 1><<<(unsigned)rs_tiles<4>(B, H, W), 128, 0, st_>>>((const A*)in1, (const A*)in2, (const A*)target, (A*)cos_out,
+                                                                                        (A*)stats, B, C, Hi, Wi, H, W, dil, static_cast<A>(eps));
     return launch_status();
 }
 
@@ -435,9 +486,16 @@ template <typename A, int NT>
 static int rs_launch_cos_bwd(const void* in1, const void* in2, const void* target, const void* stats, const void* gcos, void* gin1,
                              void* gin2, void* gval, void* gtarget, int B, int C, int Hi, int Wi, int H, int W, int dil, double eps,
                              int accumulate, cudaStream_t st_) {
-    k_resample2d_cos_bwd<A, NT><<<(unsigned)rs_tiles<4>(B, H, W), 128, 0, st_>>>(
-        (const A*)in1, (const A*)in2, (const A*)target, (const A*)stats, (const A*)gcos, (A*)gin2, (A*)gval, (A*)gtarget, B, C, Hi, Wi, H,
-        W, dil, static_cast<A>(eps), accumulate);
+    bool sliced = false;
+    if constexpr (NT <= 2) sliced = rs_cos_slices(B, C, H, W) == 4;
+    if constexpr (NT <= 2) if (sliced)
+        k_resample2d_cos_bwd<A, NT, 4><<<(unsigned)rs_tiles<1>(B, H, W), 128, 0, st_>>>(
+            (const A*)in1, (const A*)in2, (const A*)target, (const A*)stats, (const A*)gcos, (A*)gin2, (A*)gval, (A*)gtarget, B, C, Hi, Wi,
+            H, W, dil, static_cast<A>(eps), accumulate);
+    if (!sliced)
+        k_resample2d_cos_bwd<A, NT, 1><<<(unsigned)rs_tiles<4>(B, H, W), 128, 0, st_>>>(
+            (const A*)in1, (const A*)in2, (const A*)target, (const A*)stats, (const A*)gcos, (A*)gin2, (A*)gval, (A*)gtarget, B, C, Hi, Wi,
+            H, W, dil, static_cast<A>(eps), accumulate);
     int e = launch_status();
     if (e || gin1 == nullptr) return e;
     const long long total = (long long)B * H * W;
