@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         path = os.path.join(CSRC, src)
         obj = os.path.join(OBJ, src[:-3] + ".o")
         stamp = obj + ".sha"
-        flags = ARCH + COMMON + EXTRA.get(src, []) + (["-DGFLA_TC_PROFILE"] if os.environ.get("GFLA_BUILD_PROFILE") == "1" else []) \
+        flags = ARCH + COMMON + EXTRA.get(src, []) + (["-DGFLA_TC_PROFILE"] if os.environ.get("GFLA_BUILD_PROFILE") == "1" else []) + (["-DGFLA_TC_KNOBS_ON"] if os.environ.get("GFLA_BUILD_KNOBS") == "1" else []) \
             + ([f"-DGFLA_TC_WAIT_CYCLES={int(os.environ['GFLA_TC_WAIT_CYCLES'])}LL"] if os.environ.get("GFLA_TC_WAIT_CYCLES") else [])
         dig = _digest([path] + headers) + " " + " ".join(flags)
         if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:

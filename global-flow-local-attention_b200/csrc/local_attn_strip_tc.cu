@@ -105,7 +105,8 @@ k_local_attn_fwd_strip(const __grid_constant__ CUtensorMap tmap_src, const __gri
                        const float* __restrict__ flow, const __nv_bfloat16* __restrict__ logits,
                        __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ probs,
                        const __nv_bfloat16* __restrict__ prev, const __nv_bfloat16* __restrict__ mask, int B, int C, int Hs,
-                       int Ws, int H, int W, int ts, int knobs) {
+                       int Ws, int H, int W, int ts, int knobs_arg) {
+    const int knobs = GFLA_KNOBS(knobs_arg);      // 0 in the shipped build: every `knobs & x` test folds away
     // `knobs` (environment GFLA_TC_KNOBS, default 0 = production) switch parts of the pipeline off for timing experiments
     // (results are wrong when set): bit 8 no output stores, bit 10 no weight scatter (slabs only zeroed), bit 11 no slab
     // writes at all, bit 12 no MMAs, bit 13 no TMA loads, bit 14 L2 prefetch of upcoming rows ON (measured slower: 0.54 vs 0.49 ms at cfg2; off by default).

@@ -465,7 +465,8 @@ static int rs_launch_bwd(const void* in1, const void* in2, const void* gout, voi
 
 // channel slices per pixel: 4 when the map is too small to fill the machine with one thread per pixel (and C is worth splitting)
 static inline int rs_cos_slices(int B, int C, int H, int W) {
-    return (C >= 32 && (long long)B * H * W < (long long)sm_count() * 2048 * 2) ? 4 : 1;
+    // measured (bench.py f4_resample_cosine, fwd+bwd): 65 k pixels x 256 channels 0.92 -> 0.76 ms with slices, 262 k pixels x 128 channels 1.17 -> 1.56 ms
+    return (C >= 64 && (long long)B * H * W < (long long)sm_count() * 1024) ? 4 : 1;
 }
 
 template <typename A, int NT>

@@ -267,6 +267,16 @@ __device__ __forceinline__ void irregular_pixel(const __nv_bfloat16* __restrict_
     }
 }
 
+// Ablation switches of the tile kernels (GFLA_TC_KNOBS / GFLA_BWD_KNOBS, read per launch) exist only in a tuning build
+// (GFLA_BUILD_KNOBS=1 python build.py, i.e. -DGFLA_TC_KNOBS_ON).  The shipped kernels compile them out: the ~20 extra
+// branches cost the fused backward 12 % (0.99 -> 1.11 ms measured when four more were added, profiles/r2_l2_policy.md) --
+// these kernels run 6 role programs on one SM and are sensitive to code size.
+#ifdef GFLA_TC_KNOBS_ON
+#define GFLA_KNOBS(k) (k)
+#else
+#define GFLA_KNOBS(k) 0
+#endif
+
 // tuning knobs (environment, read per launch)
 inline int tune_knob(const char* name, int dflt) {
     const char* v = getenv(name);

@@ -1,0 +1,12 @@
+#!/bin/bash
+# A/B on one box: tile kernels with the ablation switches compiled out (shipped) vs compiled in (GFLA_BUILD_KNOBS=1)
+mkdir -p gpurun_out
+run() { timeout 300 python bench.py --no-e2e --no-cpu-baseline --no-extras --steps 20 2>> gpurun_out/r2q.err | python -c "
+import json,sys
+j=json.loads(sys.stdin.read()); print('$1', j['value'], 'fwd', j['roofline_fwd']['launch_ms'], 'bwd', j['roofline_bwd']['launch_ms'], 'nchw', j['planar_nchw']['ms_per_step'])"; }
+for rep in 1 2; do
+run "shipped(knobs compiled out)"
+GFLA_LIB=$PWD/gpurun_ab/libgfla_knobs_on.so run "tuning build(knobs compiled in)"
+done 2>&1 | tee gpurun_out/r2q_ab2.txt
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_resample_cosine.py -m gpu -x -q -k "tile or strip or bwd or blend or cosine" > gpurun_out/r2q_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/r2q_pytest.log
+tail -3 gpurun_out/r2q.err
