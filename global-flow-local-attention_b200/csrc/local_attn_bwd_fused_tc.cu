@@ -106,6 +106,28 @@ __device__ __forceinline__ float lds_f32(uint32_t a) {
     return v;
 }
 
+// The four channel dot products <grad_out[p,:], source[tap,:]> of one tap of an irregular pixel, warp-cooperative.  Out of line:
+// the k*k taps of the literal path are unrolled (their results index register arrays) and this body, inlined 25 times, was
+// two thirds of the kernel's 34 k instructions -- for a path that ~1e-5 of the pixels take.
+static __device__ __noinline__ float4 fb_tap_dots(const __nv_bfloat16* __restrict__ go, const __nv_bfloat16* __restrict__ sLT,
+                                                  const __nv_bfloat16* __restrict__ sRT, const __nv_bfloat16* __restrict__ sLB,
+                                                  const __nv_bfloat16* __restrict__ sRB, int C, int lane) {
+    float qLT = 0.f, qRT = 0.f, qLB = 0.f, qRB = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        const float gv = __bfloat162float(go[c]);
+        qLT += gv * __bfloat162float(sLT[c]);
+        qRT += gv * __bfloat162float(sRT[c]);
+        qLB += gv * __bfloat162float(sLB[c]);
+        qRB += gv * __bfloat162float(sRB[c]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        qLT += __shfl_xor_sync(0xffffffffu, qLT, o); qRT += __shfl_xor_sync(0xffffffffu, qRT, o);
+        qLB += __shfl_xor_sync(0xffffffffu, qLB, o); qRB += __shfl_xor_sync(0xffffffffu, qRB, o);
+    }
+    return make_float4(qLT, qRT, qLB, qRB);
+}
+
 template <int K, int CN>
 __global__ void __launch_bounds__(FB_THREADS, 1)
 k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_s,
@@ -242,7 +264,7 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
                 tile_bbox_reduce<K>(nf, ngx0, ngy0, H, W, Hs, Ws, lane, false, x0, y0, x1, y1);
                 const int pcb = (x1 - x0 + FB_BW) / FB_BW, prc = (knobs & 1) ? y1 - y0 + 1 : 0;
                 for (int i = lane; i < pcb * prc * (CN / 64); i += 32) {
-                    const int cg = i % (CN / 64), st = i / (CN / 64), cb = st / prc, rc = st - cb * prc;
+                    const int cg = i % (CN / 64), st = i / (CN / 64), cb = st / max(prc, 1), rc = st - cb * prc;
                     tma_prefetch_4d(&tmap_s, cg * 64, x0 + cb * FB_BW, y0 + rc * FB_QROWS, nb);
                 }
             }
@@ -511,19 +533,9 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
                         const AxisTap<float> axx = axis_tap<float>(qfx, j - K / 2, qx, Ws);
-                        float qLT = 0.f, qRT = 0.f, qLB = 0.f, qRB = 0.f;
-                        for (int c = lane; c < C; c += 32) {
-                            const float gv = __bfloat162float(go[c]);
-                            qLT += gv * __bfloat162float(sb[((long long)ayy.lo * Ws + axx.lo) * C + c]);
-                            qRT += gv * __bfloat162float(sb[((long long)ayy.lo * Ws + axx.hi) * C + c]);
-                            qLB += gv * __bfloat162float(sb[((long long)ayy.hi * Ws + axx.lo) * C + c]);
-                            qRB += gv * __bfloat162float(sb[((long long)ayy.hi * Ws + axx.hi) * C + c]);
-                        }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            qLT += __shfl_xor_sync(0xffffffffu, qLT, o); qRT += __shfl_xor_sync(0xffffffffu, qRT, o);
-                            qLB += __shfl_xor_sync(0xffffffffu, qLB, o); qRB += __shfl_xor_sync(0xffffffffu, qRB, o);
-                        }
+                        const float4 qd = fb_tap_dots(go, sb + ((long long)ayy.lo * Ws + axx.lo) * C, sb + ((long long)ayy.lo * Ws + axx.hi) * C,
+                                                      sb + ((long long)ayy.hi * Ws + axx.lo) * C, sb + ((long long)ayy.hi * Ws + axx.hi) * C, C, lane);
+                        const float qLT = qd.x, qRT = qd.y, qLB = qd.z, qRB = qd.w;
                         if (lane == sl) {  // the owner keeps the results (its pp[] is the right softmax)
                             dp[i * K + j] = inv_kk * (ayy.wlo * (axx.wlo * qLT + axx.whi * qRT) + ayy.whi * (axx.wlo * qLB + axx.whi * qRB));
                             const float pij = pp[i * K + j] * inv_kk;

@@ -46,7 +46,7 @@ static __device__ unsigned long long* g_tc_dbg = nullptr;
 #ifndef GFLA_TC_WAIT_CYCLES
 #define GFLA_TC_WAIT_CYCLES 20000000000LL
 #endif
-static __device__ __noinline__ void mbar_timeout(uint32_t tag, uint32_t parity, uint32_t iter) {
+static __device__ __noinline__ __attribute__((noreturn)) void mbar_timeout(uint32_t tag, uint32_t parity, uint32_t iter) {
     unsigned long long* d = g_tc_dbg;
     if (d != nullptr) {
         if (atomicCAS(d, 0ull, (unsigned long long)tag | (1ull << 63)) == 0ull) {
@@ -55,6 +55,7 @@ static __device__ __noinline__ void mbar_timeout(uint32_t tag, uint32_t parity, 
         __threadfence_system();
     }
     __trap();
+    __builtin_unreachable();     // noreturn: no wait site has to keep its registers alive across this call
 }
 // Wait profile (debug builds only: GFLA_BUILD_PROFILE=1 python build.py, i.e. -DGFLA_TC_PROFILE): cycles that
 // lane 0 of every warp spent blocked, per (role, barrier kind) of the tag, plus explicit region timers (kinds 6, 7);
