@@ -175,6 +175,15 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
     const long long t_start = tc_profile_clock();
     const int gxn = (W + GW - 1) / GW, gyn = (H + GH - 1) / GH;
     const int ngroups = B * gyn * gxn;
+    FastDiv fdx, fdy;
+    fdx.init((uint32_t)gxn);
+    fdy.init((uint32_t)gyn);
+    auto split = [&](int g, int& gx, int& gy, int& b) {      // group index -> (column, row, sample) of the group
+        uint32_t q, r, q2, r2;
+        fdx.divmod((uint32_t)g, q, r);
+        fdy.divmod(q, q2, r2);
+        gx = (int)r; gy = (int)r2; b = (int)q2;
+    };
     const long long hw = (long long)H * W;
 
     if (threadIdx.x == 0) {
@@ -212,11 +221,14 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         int gi = 0;
         int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
         if (blockIdx.x < ngroups) {
-            const int g = blockIdx.x;
-            group_bbox<K>(flow, g / (gxn * gyn), (g % gxn) * GW, ((g / gxn) % gyn) * GH, H, W, Hs, Ws, lane, false, x0, y0, x1, y1);
+            int gx, gy, b;
+            split((int)blockIdx.x, gx, gy, b);
+            group_bbox<K>(flow, b, gx * GW, gy * GH, H, W, Hs, Ws, lane, false, x0, y0, x1, y1);
         }
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
-            const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
+            int gxi, gyi, b;
+            split(g, gxi, gyi, b);
+            const int gx0 = gxi * GW, gy0 = gyi * GH;
             const int ncb = (x1 - x0 + FB_BW) / FB_BW, nrows = y1 - y0 + 1, nst = ncb * nrows;
             if (lane == 0) {
                 if (cur_sample != nullptr) *cur_sample = (unsigned int)b;
@@ -226,12 +238,16 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             }
             const int gn = g + gridDim.x;
             const bool has_next = gn < ngroups;
-            const int ngx0 = (gn % gxn) * GW, ngy0 = ((gn / gxn) % gyn) * GH, nb = gn / (gxn * gyn);
+            int ngxi = 0, ngyi = 0, nb = 0;
+            if (has_next) split(gn, ngxi, ngyi, nb);
+            const int ngx0 = ngxi * GW, ngy0 = ngyi * GH;
             TileFlow nf;
             if (has_next) tile_flow_load(flow, nb, ngx0, ngy0, H, W, lane, nf);
             const int cx0 = x0, cy0 = y0;
-            auto load_stage = [&](int s) {
-                const int cb = s / nrows, rc = s - cb * nrows, slot = it % NS;
+            int st_cb = 0, st_rc = 0;                           // column block / row of the next stage (stages run down the rows of a block)
+            auto load_stage = [&](int) {
+                const int cb = st_cb, rc = st_rc, slot = it % NS;
+                if (++st_rc == nrows) { st_rc = 0; ++st_cb; }
                 mbar_wait(&s_empty[slot], ((it / NS) & 1) ^ 1, 0x000200 | slot, it);
                 if ((knobs & 64) && lane == 0) mbar_arrive(&s_full[slot]);
                 if (!(knobs & 64) && elect_one()) {
@@ -388,7 +404,9 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         int gi = 0;
         float pfx = 0.f, pfy = 0.f;          // flow of this thread's pixel, loaded one group ahead
         auto load_pixel = [&](int g) {
-            const int px = (g % gxn) * GW + (m & 15), py = ((g / gxn) % gyn) * GH + (m >> 4), b = g / (gxn * gyn);
+            int gxi, gyi, b;
+            split(g, gxi, gyi, b);
+            const int px = gxi * GW + (m & 15), py = gyi * GH + (m >> 4);
             if (px < W && py < H) {
                 const long long pofs = (long long)py * W + px;
                 pfx = flow[(long long)b * 2 * hw + pofs];
@@ -397,7 +415,9 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         };
         if (blockIdx.x < ngroups) load_pixel(blockIdx.x);
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
-            const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH;
+            int gxi, gyi, b_unused;
+            split(g, gxi, gyi, b_unused);
+            const int gx0 = gxi * GW, gy0 = gyi * GH;
             const int px = gx0 + (m & 15), py = gy0 + (m >> 4);
             const bool live = px < W && py < H;      // irregular pixels are extracted too (their values are ignored by the builders)
             // window origin = unclamped floor of the first tap (block_extractor_kernel.cu:62-66)
@@ -471,7 +491,9 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         __nv_bfloat16 lg[KK];
         float pfx = 0.f, pfy = 0.f;
         auto load_pixel = [&](int g) {
-            const int px = (g % gxn) * GW + (m & 15), py = ((g / gxn) % gyn) * GH + (m >> 4), b = g / (gxn * gyn);
+            int gxi, gyi, b;
+            split(g, gxi, gyi, b);
+            const int px = gxi * GW + (m & 15), py = gyi * GH + (m >> 4);
             if (px < W && py < H) {
                 const long long pofs = (long long)py * W + px;
                 const __nv_bfloat16* lp = logits + (long long)b * KK * hw + pofs;
@@ -564,7 +586,9 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         };
         if (blockIdx.x < ngroups) load_pixel(blockIdx.x);
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
-            const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
+            int gxi, gyi, b;
+            split(g, gxi, gyi, b);
+            const int gx0 = gxi * GW, gy0 = gyi * GH;
             const int px = gx0 + (m & 15), py = gy0 + (m >> 4);
             const bool valid = px < W && py < H;
             int X0 = 0, Y0 = 0;
@@ -623,7 +647,9 @@ k_local_attn_bwd_fused(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         uint32_t u = 0, oi = 0;   // oi: running index of the staging tile (alternates between the two buffers)
         int gi = 0, zeroed_b = -1;
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x, ++gi) {
-            const int gx0 = (g % gxn) * GW, gy0 = ((g / gxn) % gyn) * GH, b = g / (gxn * gyn);
+            int gxi, gyi, b;
+            split(g, gxi, gyi, b);
+            const int gx0 = gxi * GW, gy0 = gyi * GH;
             if (zero_flags != nullptr && b != zeroed_b) {      // first adds into this sample: its zero-fill must be complete
                 if (lane == 0) {
                     unsigned int seen;

@@ -192,6 +192,22 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, in
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+// Division of tile / group indices by run-time image geometry: magic multiplier computed once per thread at kernel start, then
+// umulhi + shift per use (an integer division is ~25 dependent instructions, and every role decodes its group index per group).
+// Exact for 0 <= n < 2^31, d >= 1.
+struct FastDiv {
+    uint32_t d, mul, shr;
+    __device__ __forceinline__ void init(uint32_t div) {
+        d = div;
+        if (div <= 1) { mul = 0; shr = 0; return; }
+        const uint32_t p = 31 + (32 - __clz(div - 1));           // 31 + ceil(log2(div))
+        mul = static_cast<uint32_t>(((1ull << p) + div - 1) / div);
+        shr = p - 32;
+    }
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d != 1 ? __umulhi(n, mul) >> shr : n; }
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const { q = div(n); r = n - q * d; }
+};
+
 // One lane of a converged warp (the same one every time).  MMA issue must branch on THIS, not on `lane == 0`: after
 // elect.sync the compiler knows a single lane is live and moves descriptors to the uniform registers UTCHMMA wants with
 // one R2UR each; behind a plain lane test it emits a waterfall loop (ELECT / R2UR.BROADCAST / BRA.U.ANY) per operand,
