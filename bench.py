@@ -531,12 +531,13 @@ def main():
                 "algorithmic_bytes": nbytes, "launch_ms": ms}
 
     rf_fwd = roof(fwd_bytes, fwd_ms, "k_local_attn_fwd_strip (fused forward)", "fwd")
-    rf_bwd = roof(bwd_bytes, bwd_ms, "k_local_attn_bwd_gs_tc + k_local_attn_bwd_q_tc (+ grad_source memset)", "bwd")
-    # The step is three tile kernels of similar weight (ncu launch list, profiles/r1_bench_launches.md:
-    # grad_flow/logits 36 %, forward 34 %, grad_source 30 %).  `roofline` describes the fused FORWARD kernel --
-    # a single launch with clean algorithmic bytes, and the one the north-star target is stated on;
-    # `roofline_bwd` is the backward as a unit (its two kernels + the grad_source memset, timed together).
-    dominant = dict(rf_fwd, share_of_step=fwd_ms / ms_per_step)
+    fused_bwd = os.environ.get("GFLA_BWD_FUSED", "1") != "0"
+    rf_bwd = roof(bwd_bytes, bwd_ms, "k_local_attn_bwd_fused (fused backward, zero fill of grad_source inside the kernel)" if fused_bwd
+                  else "k_local_attn_bwd_gs_tc + k_local_attn_bwd_q_tc + grad_source memset", "bwd")
+    rf_fwd["share_of_step"], rf_bwd["share_of_step"] = fwd_ms / ms_per_step, bwd_ms / ms_per_step
+    # The step is two launches: the fused forward (~1/3 of the time) and the fused backward (~2/3; ncu launch list:
+    # profiles/r2_bench_launches.md).  `roofline` describes the DOMINANT one by measured share; both are always reported.
+    dominant = dict(rf_bwd if bwd_ms >= fwd_ms else rf_fwd)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": config,
