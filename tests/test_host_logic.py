@@ -28,3 +28,23 @@ def test_feature_layout_detection():
     assert F_._feature_layout(x.contiguous(memory_format=torch.channels_last)) == _lib.GFLA_NHWC
     with pytest.raises(AssertionError):
         F_._feature_layout(x[:, ::2])
+
+
+def test_fastdiv_multiply_shift_is_exact():
+    """tc_common.cuh `FastDiv` (group index -> (column, row, sample) in the fused backward): q = umulhi(n, mul) >> shr with
+    p = 31 + ceil(log2 d), mul = ceil(2^p / d) (always < 2^32), shr = p - 32 must equal n // d for every 0 <= n < 2^31.
+    The formula is restated here and checked for the divisors the kernels can meet (group columns / rows) at boundary and random n."""
+    import random
+
+    def make(d):
+        p = 31 + (d - 1).bit_length()                 # 32 - clz(d - 1) == bit_length(d - 1)
+        m = ((1 << p) + d - 1) // d
+        assert m < (1 << 32), d                       # the device keeps it in a uint32_t
+        return m, p - 32
+
+    rng = random.Random(7)
+    divisors = list(range(2, 70)) + [rng.randrange(70, 1 << 16) for _ in range(300)] + [255, 256, 257, 4095, 4096, 65535, 65536, (1 << 20) + 3]
+    for d in divisors:
+        mul, shr = make(d)
+        for n in [0, 1, d - 1, d, d + 1, 2 * d - 1, (1 << 31) - 1, (1 << 31) - d] + [rng.randrange(0, 1 << 31) for _ in range(200)]:
+            assert ((n * mul) >> 32) >> shr == n // d, (n, d)
