@@ -324,6 +324,8 @@ def main():
     ap.add_argument("--algo", default="auto", choices=["auto", "gather", "tile"])
     ap.add_argument("--layout", default="nhwc", choices=["nhwc", "nchw"],
                     help="storage of the [B,C,H,W] feature tensors: channels_last (default, the tile kernels' fast layout) or contiguous NCHW")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="e2e leg: number of batch chunks per step")
+    ap.add_argument("--e2e-streams", type=int, default=2, help="e2e leg: CUDA streams the chunks alternate between")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4", "cfg5"],
                     help="cfg2 (default, the BASELINE metric): fused warp layer fwd+bwd; cfg4 / cfg5: the reference's Pose / Face generator on these ops (bench_models.py)")
     ap.add_argument("--model-dtype", default="bf16", choices=["bf16", "fp32"], help="cfg4/cfg5: parameter / activation dtype")
@@ -464,15 +466,16 @@ def main():
         h2d = sum(t.numel() * t.element_size() for t in (hs, hf, hl, hg))
         d2h = sum(t.numel() * t.element_size() for t in (ho, hgs, hgf, hgl))
 
-        # The batch is processed in 4-sample chunks alternating between 2 streams, so the H2D of chunk i+1 overlaps the
+        # The batch is processed in chunks (default 4 of 4 samples) alternating between streams (default 2), so the H2D of chunk i+1 overlaps the
         # kernels and the D2H of chunk i (PCIe is full duplex; every byte is still copied inside the timed region, through
         # the public autograd API, once per step).  The two streams are joined to the timing stream once in front of the
         # first step and once behind the last one -- consecutive steps pipeline like consecutive chunks (a chunk always
         # returns to the stream that handled the same host slices in the previous step, so host buffers are reused in order).
         # Host buffers are pinned on the GPU's own NUMA node (see above).
-        chunks = [(b0, min(B, b0 + 4)) for b0 in range(0, B, 4)]
-        side = [torch.cuda.Stream(device=dev) for _ in range(2)]
-        assert len(chunks) % len(side) == 0 or len(chunks) == 1
+        per = max(1, B // max(1, args.e2e_chunks))
+        chunks = [(b0, min(B, b0 + per)) for b0 in range(0, B, per)]
+        side = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(args.e2e_streams, len(chunks))))]
+        assert len(chunks) % len(side) == 0, "chunks must be a multiple of streams (a host slice always returns to the same stream)"
 
         def e2e_steps_run(n):
             main = torch.cuda.current_stream(dev)
@@ -480,7 +483,7 @@ def main():
                 st.wait_stream(main)
             for _ in range(n):
                 for ci, (b0, b1) in enumerate(chunks):
-                    with torch.cuda.stream(side[ci % 2]):
+                    with torch.cuda.stream(side[ci % len(side)]):
                         s = hs[b0:b1].to(dev, non_blocking=True).requires_grad_()
                         f = hf[b0:b1].to(dev, non_blocking=True).requires_grad_()
                         l = hl[b0:b1].to(dev, non_blocking=True).requires_grad_()
