@@ -832,10 +832,26 @@ static int launch_fused(const void* src, const void* flow, const void* logits, c
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (zero_flags != nullptr && tune_knob("GFLA_BWD_COOP", 1) != 0) ? 1 : 0;      // (the switch exists for A/B timing only)
-    e = cudaLaunchKernelEx(&cfg, kern, tg, ts, tgs, (const __nv_bfloat16*)src, (const float*)flow, (const __nv_bfloat16*)logits,
-                           (const __nv_bfloat16*)gout, (__nv_bfloat16*)gsrc, (float*)gflow, (__nv_bfloat16*)glogits, B, C, Hs, Ws, H, W,
-                           accumulate, (int)tune_knob("GFLA_BWD_KNOBS", 0), zero_flags);
+    const int knobs_env = (int)tune_knob("GFLA_BWD_KNOBS", 0);
+    auto launch = [&](unsigned int* zf, bool coop) -> cudaError_t {
+        cfg.numAttrs = coop ? 1 : 0;
+        return cudaLaunchKernelEx(&cfg, kern, tg, ts, tgs, (const __nv_bfloat16*)src, (const float*)flow, (const __nv_bfloat16*)logits,
+                                  (const __nv_bfloat16*)gout, (__nv_bfloat16*)gsrc, (float*)gflow, (__nv_bfloat16*)glogits, B, C, Hs, Ws, H, W,
+                                  accumulate, knobs_env, zf);
+    };
+    // GFLA_BWD_COOP: 1 (default) cooperative; 0 plain launch of the dependent grid (A/B timing on an otherwise idle GPU only);
+    // 2 behave as if the cooperative launch had been refused (exercises the path below)
+    const int coop_mode = zero_flags != nullptr ? (int)tune_knob("GFLA_BWD_COOP", 1) : 0;
+    e = coop_mode == 2 ? cudaErrorCooperativeLaunchTooLarge : launch(zero_flags, coop_mode == 1);
+    if (zero_flags != nullptr && (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported)) {
+        // The device cannot hold the whole grid at once (an MPS client with a reduced SM share, a partitioned GPU) or has no cooperative
+        // launch: then the CTAs must not depend on each other -- zero grad_source with a memset and run the same kernel without the
+        // in-kernel zero fill (independent CTAs, any number resident).
+        cudaGetLastError();
+        const int z = zero_async(gsrc, (size_t)B * C * Hs * Ws * 2, st_);
+        if (z != GFLA_OK) return z;
+        e = launch(nullptr, false);
+    }
     if (e != cudaSuccess) { cudaGetLastError(); return static_cast<int>(e); }
     return launch_status();
 }
