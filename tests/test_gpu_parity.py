@@ -550,6 +550,22 @@ def test_local_attn_bwd_tile_many_samples_few_groups(F_, oracle_lib, shape):
     np.testing.assert_allclose(host(gf), ogf, rtol=2e-2, atol=2e-2 * max(1.0, float(np.abs(ogf).max())))
 
 
+def test_local_attn_bwd_cooperative_launch_refused_falls_back(F_, oracle_lib, monkeypatch):
+    """GFLA_BWD_COOP=2 makes the library behave as if the driver had refused the cooperative launch of the fused backward (an MPS
+    client with a reduced SM share): it must zero grad_source with a memset and run the kernel with independent CTAs -- same results."""
+    monkeypatch.setenv("GFLA_BWD_COOP", "2")
+    B, C, H, W, k = 5, 128, 24, 40, 5
+    s, f, l = _tile_inputs(B, C, H, W, H, W, k, "smooth", seed=77)
+    s = s.contiguous(memory_format=torch.channels_last)
+    rng = np.random.default_rng(5)
+    g = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32)).to(DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    gs, gf, gl = F_.local_attn_bwd(s, f, l, g, k, algo="tile")
+    ogs, ogf, ogl = oracle_lib.local_attn_bwd(host(s), f.cpu().numpy(), host(l), host(g), k)
+    np.testing.assert_allclose(host(gs), ogs, rtol=0, atol=1e-2 * max(1.0, float(np.abs(ogs).max())))
+    np.testing.assert_allclose(host(gl), ogl, rtol=0, atol=1e-2)
+    np.testing.assert_allclose(host(gf), ogf, rtol=2e-2, atol=2e-2 * max(1.0, float(np.abs(ogf).max())))
+
+
 def test_local_attn_bwd_tile_irregular_taps(F_, oracle_lib):
     rng = np.random.default_rng(43)
     B, C, H, W, k = 1, 64, 24, 64, 5
