@@ -48,3 +48,14 @@ def test_fastdiv_multiply_shift_is_exact():
         mul, shr = make(d)
         for n in [0, 1, d - 1, d, d + 1, 2 * d - 1, (1 << 31) - 1, (1 << 31) - d] + [rng.randrange(0, 1 << 31) for _ in range(200)]:
             assert ((n * mul) >> 32) >> shr == n // d, (n, d)
+
+
+def test_resample2d_cosine_has_no_cpu_path():
+    """like the reference's ops (block_extractor.py:23-24): CPU tensors raise instead of silently running somewhere else"""
+    import gfla_b200
+    x, t = torch.randn(1, 4, 8, 8), torch.randn(1, 4, 8, 8)
+    flow = torch.zeros(1, 2, 8, 8)
+    with pytest.raises(NotImplementedError):
+        gfla_b200.Resample2dCosine(4, 1, sigma=2)(x, flow, t)
+    with pytest.raises(NotImplementedError):
+        gfla_b200.Resample2d(4, 1, sigma=2)(x, flow)
