@@ -1,4 +1,6 @@
 #!/bin/bash
+# gpurun_ab/*.so are variant builds made on the build host before the call (git worktree of the variant -> build.py -> copy;
+# GFLA_BUILD_PROFILE=1 / GFLA_BUILD_KNOBS=1 for the profile / tuning builds); the directory is git-ignored (*.so) and not kept.
 # round 2, final visit with the shipped build: full GPU suite, sanitizer, the bench line, ncu captures + launch list, wait profile
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit,driver_version --format=csv > gpurun_out/r2f_gpu.txt

@@ -1,4 +1,6 @@
 #!/bin/bash
+# gpurun_ab/*.so are variant builds made on the build host before the call (git worktree of the variant -> build.py -> copy;
+# GFLA_BUILD_PROFILE=1 / GFLA_BUILD_KNOBS=1 for the profile / tuning builds); the directory is git-ignored (*.so) and not kept.
 # A/B on one box: working tree vs the committed HEAD build (gpurun_ab/libgfla_head.so), then the GPU suite
 mkdir -p gpurun_out
 run() { timeout 300 python bench.py --no-e2e --no-cpu-baseline --no-extras --steps 20 2>> gpurun_out/r2r.err | python -c "
